@@ -1,0 +1,702 @@
+// tvd_abi.cu -- the C ABI of libtvd.so (include/tvd.h): model handles, per-device contexts,
+// workspaces and the orchestration  K1 -> K4 -> Phase A -> sort -> Phase B -> Phase C.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "tvd_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors, counters
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+static std::mutex g_far_mu;
+static double g_far_ms = 0.0;
+static int64_t g_far_launches = 0;
+
+void tvd_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int set_error(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            char _buf[512];                                                                     \
+            snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                       \
+            g_last_error = _buf;                                                                \
+            cudaGetLastError();                                                                 \
+            return (int)_e;                                                                     \
+        }                                                                                       \
+    } while (0)
+
+// grow-only device buffer
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess)
+            cap = bytes;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct DeviceCtx {
+    int device = -1;
+    bool has_table = false;
+    PieceTable tab;
+    int packed_field = -1;
+    double packed_ratio = 0.0;
+    Buf test_rec, glq_rec;
+    Buf far_out, queue, keys_sorted, pair_result, sort_temp, counters;
+    Buf pts, result, counts;
+    unsigned long long qcap_hint = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+};
+
+struct tvd_model {
+    int64_t n_tess = 0, n_pieces = 0;
+    double delta = 0.0;
+    int has_delta = 0;
+    std::vector<double> h_bounds, h_params, h_top, h_bottom;
+    std::vector<int32_t> h_kind, h_npieces, h_parent;
+    std::map<int, DeviceCtx *> ctx;
+    std::mutex mu;
+};
+
+static void free_table(PieceTable &t)
+{
+    cudaFree(t.tess_bounds);
+    cudaFree(t.tess_kind);
+    cudaFree(t.tess_params);
+    cudaFree(t.tess_npieces);
+    cudaFree(t.top);
+    cudaFree(t.bottom);
+    cudaFree(t.parent);
+    t = PieceTable();
+}
+
+static void free_ctx(DeviceCtx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    free_table(c->tab);
+    c->test_rec.release();
+    c->glq_rec.release();
+    c->far_out.release();
+    c->queue.release();
+    c->keys_sorted.release();
+    c->pair_result.release();
+    c->sort_temp.release();
+    c->counters.release();
+    c->pts.release();
+    c->result.release();
+    c->counts.release();
+    if (c->ev0)
+        cudaEventDestroy(c->ev0);
+    if (c->ev1)
+        cudaEventDestroy(c->ev1);
+    if (c->stream)
+        cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int upload_tess(tvd_model *m, DeviceCtx *c)
+{
+    PieceTable &t = c->tab;
+    t.n_tess = m->n_tess;
+    const size_t nt = (size_t)(m->n_tess > 0 ? m->n_tess : 1);
+    CUDA_TRY(cudaMalloc(&t.tess_bounds, nt * 6 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t.tess_kind, nt * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&t.tess_params, nt * TVD_NPAR * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t.tess_npieces, nt * sizeof(int32_t)));
+    if (m->n_tess > 0) {
+        CUDA_TRY(cudaMemcpy(t.tess_bounds, m->h_bounds.data(), m->n_tess * 6 * sizeof(double),
+                            cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(t.tess_kind, m->h_kind.data(), m->n_tess * sizeof(int32_t),
+                            cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(t.tess_params, m->h_params.data(),
+                            m->n_tess * TVD_NPAR * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return TVD_OK;
+}
+
+static int alloc_pieces(PieceTable &t, int64_t n_pieces)
+{
+    t.n_pieces = n_pieces;
+    const size_t np = (size_t)(n_pieces > 0 ? n_pieces : 1);
+    CUDA_TRY(cudaMalloc(&t.top, np * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t.bottom, np * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t.parent, np * sizeof(int32_t)));
+    return TVD_OK;
+}
+
+static int new_ctx(int device, DeviceCtx **out)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    DeviceCtx *c = new DeviceCtx();
+    c->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess)
+        e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        free_ctx(c);
+        CUDA_TRY(e);
+    }
+    *out = c;
+    return TVD_OK;
+}
+
+// context of `device`, replicating the piece table from the host copy if needed
+static int get_ctx(tvd_model *m, int device, DeviceCtx **out)
+{
+    std::lock_guard<std::mutex> lock(m->mu);
+    auto it = m->ctx.find(device);
+    if (it != m->ctx.end()) {
+        *out = it->second;
+        return TVD_OK;
+    }
+    DeviceCtx *c = nullptr;
+    int rc = new_ctx(device, &c);
+    if (rc)
+        return rc;
+    rc = upload_tess(m, c);
+    if (!rc)
+        rc = alloc_pieces(c->tab, m->n_pieces);
+    if (!rc && m->n_pieces > 0) {
+        cudaError_t e = cudaMemcpy(c->tab.top, m->h_top.data(), m->n_pieces * sizeof(double),
+                                   cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(c->tab.bottom, m->h_bottom.data(), m->n_pieces * sizeof(double),
+                           cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(c->tab.parent, m->h_parent.data(), m->n_pieces * sizeof(int32_t),
+                           cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && m->n_tess > 0)
+            e = cudaMemcpy(c->tab.tess_npieces, m->h_npieces.data(),
+                           m->n_tess * sizeof(int32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            g_last_error = std::string("piece table replication failed: ") + cudaGetErrorString(e);
+            rc = (int)e;
+        }
+    }
+    if (rc) {
+        free_ctx(c);
+        return rc;
+    }
+    c->has_table = true;
+    m->ctx[device] = c;
+    *out = c;
+    return TVD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ABI: misc
+// ---------------------------------------------------------------------------------------------
+extern "C" int tvd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" const char *tvd_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int64_t tvd_launch_count(int reset)
+{
+    if (reset)
+        return g_launches.exchange(0);
+    return g_launches.load();
+}
+
+extern "C" double tvd_far_kernel_ms(int reset, int64_t *n_launches)
+{
+    std::lock_guard<std::mutex> lock(g_far_mu);
+    const double ms = g_far_ms;
+    if (n_launches)
+        *n_launches = g_far_launches;
+    if (reset) {
+        g_far_ms = 0.0;
+        g_far_launches = 0;
+    }
+    return ms;
+}
+
+extern "C" double tvd_measure_fp64_peak(int device, int iters)
+{
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1.0;
+    }
+    return tvd_fp64_probe(iters > 0 ? iters : 4096, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ABI: model
+// ---------------------------------------------------------------------------------------------
+extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int32_t *kind,
+                                const double *params, double delta, int device, tvd_model **out)
+{
+    g_last_error.clear();
+    if (!out || n_tess < 0 || (n_tess > 0 && (!bounds || !kind || !params)))
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_model_create: bad argument");
+    if (n_tess > 0x7fffffffLL)
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_model_create: more than 2^31-1 tesseroids");
+    *out = nullptr;
+    if (tvd_device_count() <= device || device < 0)
+        return set_error(TVD_ERR_NO_DEVICE, "tvd_model_create: no such CUDA device (no CPU fallback)");
+    for (int64_t i = 0; i < n_tess; i++)
+        if (kind[i] < TVD_DENS_CONST || kind[i] > TVD_DENS_SINE)
+            return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_model_create: unknown density kind");
+
+    tvd_model *m = new tvd_model();
+    m->n_tess = n_tess;
+    m->has_delta = std::isnan(delta) ? 0 : 1;
+    m->delta = m->has_delta ? delta : 0.0;
+    m->h_bounds.assign(bounds, bounds + 6 * n_tess);
+    m->h_kind.assign(kind, kind + n_tess);
+    m->h_params.assign(params, params + TVD_NPAR * n_tess);
+
+    DeviceCtx *c = nullptr;
+    int rc = new_ctx(device, &c);
+    if (rc) {
+        delete m;
+        return rc;
+    }
+    auto fail = [&](int code) {
+        free_ctx(c);
+        delete m;
+        return code;
+    };
+    rc = upload_tess(m, c);
+    if (rc)
+        return fail(rc);
+    int *d_status = nullptr;
+    int64_t *d_offsets = nullptr;
+    auto cleanup_tmp = [&]() {
+        cudaFree(d_status);
+        cudaFree(d_offsets);
+    };
+#define MODEL_TRY(expr)                                                                  \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            g_last_error = std::string(#expr " failed: ") + cudaGetErrorString(_e);      \
+            cudaGetLastError();                                                          \
+            cleanup_tmp();                                                               \
+            return fail((int)_e);                                                        \
+        }                                                                                \
+    } while (0)
+    MODEL_TRY(cudaMalloc(&d_status, sizeof(int)));
+    MODEL_TRY(cudaMalloc(&d_offsets, (size_t)(n_tess + 1) * sizeof(int64_t)));
+    MODEL_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), c->stream));
+    MODEL_TRY(tvd_launch_k1_count(c->tab, m->delta, m->has_delta, d_status, c->stream));
+    MODEL_TRY(tvd_launch_scan(c->tab.tess_npieces, d_offsets, n_tess, c->stream));
+    int64_t total = 0;
+    int status = 0;
+    MODEL_TRY(cudaMemcpyAsync(&total, d_offsets + n_tess, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                              c->stream));
+    MODEL_TRY(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MODEL_TRY(cudaStreamSynchronize(c->stream));
+    if (status != 0) {
+        cleanup_tmp();
+        set_error(status, "tvd_model_create: a tesseroid needs more than 256 radial pieces "
+                          "(delta too small for this density)");
+        return fail(status);
+    }
+    if (total > 0xffffffffLL) {
+        cleanup_tmp();
+        set_error(TVD_ERR_TOO_MANY_PIECES, "tvd_model_create: more than 2^32-1 radial pieces");
+        return fail(TVD_ERR_TOO_MANY_PIECES);
+    }
+    m->n_pieces = total;
+    rc = alloc_pieces(c->tab, total);
+    if (rc) {
+        cleanup_tmp();
+        return fail(rc);
+    }
+    MODEL_TRY(tvd_launch_k1_emit(c->tab, d_offsets, m->delta, m->has_delta, c->stream));
+    m->h_top.resize(total);
+    m->h_bottom.resize(total);
+    m->h_parent.resize(total);
+    m->h_npieces.resize(n_tess);
+    if (total > 0) {
+        MODEL_TRY(cudaMemcpyAsync(m->h_top.data(), c->tab.top, total * sizeof(double),
+                                  cudaMemcpyDeviceToHost, c->stream));
+        MODEL_TRY(cudaMemcpyAsync(m->h_bottom.data(), c->tab.bottom, total * sizeof(double),
+                                  cudaMemcpyDeviceToHost, c->stream));
+        MODEL_TRY(cudaMemcpyAsync(m->h_parent.data(), c->tab.parent, total * sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, c->stream));
+        MODEL_TRY(cudaMemcpyAsync(m->h_npieces.data(), c->tab.tess_npieces,
+                                  n_tess * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    MODEL_TRY(cudaStreamSynchronize(c->stream));
+#undef MODEL_TRY
+    cleanup_tmp();
+    c->has_table = true;
+    m->ctx[device] = c;
+    *out = m;
+    return TVD_OK;
+}
+
+extern "C" void tvd_model_free(tvd_model *m)
+{
+    if (!m)
+        return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &kv : m->ctx)
+        free_ctx(kv.second);
+    cudaSetDevice(cur);
+    delete m;
+}
+
+extern "C" int64_t tvd_model_num_pieces(const tvd_model *m) { return m ? m->n_pieces : 0; }
+
+extern "C" int tvd_model_get_pieces(const tvd_model *m, double *top, double *bottom,
+                                    int32_t *parent)
+{
+    if (!m)
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_model_get_pieces: null model");
+    if (top)
+        memcpy(top, m->h_top.data(), m->n_pieces * sizeof(double));
+    if (bottom)
+        memcpy(bottom, m->h_bottom.data(), m->n_pieces * sizeof(double));
+    if (parent)
+        memcpy(parent, m->h_parent.data(), m->n_pieces * sizeof(int32_t));
+    return TVD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// summation plan
+// ---------------------------------------------------------------------------------------------
+static int plan_groups(int64_t n_pieces, int64_t n_points_total)
+{
+    // Enough thread blocks for ~2 waves of 4 resident 128-thread blocks on 148 SMs, but never
+    // groups smaller than 4 tiles.  Pure function of (Q, P_total).
+    const int64_t blocks_x = (n_points_total + 127) / 128;
+    if (blocks_x <= 0 || n_pieces <= 0)
+        return 1;
+    const int64_t want = 148 * 4 * 2;
+    int64_t g = (want + blocks_x - 1) / blocks_x;
+    const int64_t gmax = n_pieces / (4 * TVD_TILE);
+    if (g > gmax)
+        g = gmax;
+    if (g < 1)
+        g = 1;
+    if (g > 65535)
+        g = 65535;
+    return (int)g;
+}
+
+extern "C" int tvd_plan_groups(const tvd_model *m, int64_t n_points_total)
+{
+    return m ? plan_groups(m->n_pieces, n_points_total) : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward on one device (device pointers), the core
+// ---------------------------------------------------------------------------------------------
+static int forward_core(tvd_model *m, DeviceCtx *c, int field, int64_t P, const double *d_lon,
+                        const double *d_sinlat, const double *d_coslat, const double *d_radius,
+                        double ratio, int stack_size, int n_groups, double *d_result,
+                        int64_t *stats, int32_t *d_leaf_counts, cudaStream_t stream)
+{
+    const int64_t Q = m->n_pieces;
+    if (stats)
+        memset(stats, 0, TVD_NSTATS * sizeof(int64_t));
+    if (P == 0)
+        return TVD_OK;
+    if (P > 0x7fffffffLL)
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: more than 2^31-1 points per device");
+    if (Q == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_result, 0, P * sizeof(double), stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        return TVD_OK;
+    }
+    if (n_groups <= 0)
+        n_groups = plan_groups(Q, P);
+    int64_t ppg = (Q + n_groups - 1) / n_groups;
+    ppg = ((ppg + TVD_TILE - 1) / TVD_TILE) * TVD_TILE;
+    // groups that would start beyond Q are dropped (they would add exact zeros)
+    n_groups = (int)((Q + ppg - 1) / ppg);
+
+    // K4: root records for (field, ratio), cached
+    if (c->packed_field != field || c->packed_ratio != ratio) {
+        CUDA_TRY(c->test_rec.reserve((size_t)Q * TVD_TEST_REC * sizeof(double)));
+        CUDA_TRY(c->glq_rec.reserve((size_t)Q * TVD_GLQ_REC * sizeof(double)));
+        CUDA_TRY(tvd_launch_pack(field, c->tab, ratio, c->test_rec.as<double>(),
+                                 c->glq_rec.as<double>(), stream));
+        c->packed_field = field;
+        c->packed_ratio = ratio;
+    }
+    CUDA_TRY(c->far_out.reserve((size_t)n_groups * P * sizeof(double)));
+    CUDA_TRY(c->counters.reserve(16 * sizeof(unsigned long long)));
+    unsigned long long qcap = c->qcap_hint;
+    if (qcap == 0) {
+        qcap = 16ull * (unsigned long long)P;
+        if (qcap < (1ull << 20))
+            qcap = 1ull << 20;
+    }
+    const unsigned long long all_pairs = (unsigned long long)P * (unsigned long long)Q;
+    if (qcap > all_pairs)
+        qcap = all_pairs;
+
+    unsigned long long *d_cnt = c->counters.as<unsigned long long>();   // [0]=queue count, [8..]=near
+    unsigned long long nq = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CUDA_TRY(c->queue.reserve((size_t)qcap * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), stream));
+        FarArgs fa;
+        fa.field = field;
+        fa.n_points = P;
+        fa.lon = d_lon;
+        fa.sinlat = d_sinlat;
+        fa.coslat = d_coslat;
+        fa.radius = d_radius;
+        fa.n_pieces = Q;
+        fa.test_rec = c->test_rec.as<double>();
+        fa.glq_rec = c->glq_rec.as<double>();
+        fa.n_groups = n_groups;
+        fa.pieces_per_group = ppg;
+        fa.far_out = c->far_out.as<double>();
+        fa.queue = c->queue.as<unsigned long long>();
+        fa.qcount = d_cnt;
+        fa.qcap = qcap;
+        CUDA_TRY(cudaEventRecord(c->ev0, stream));
+        CUDA_TRY(tvd_launch_far(fa, stream));
+        CUDA_TRY(cudaEventRecord(c->ev1, stream));
+        CUDA_TRY(cudaMemcpyAsync(&nq, d_cnt, sizeof(nq), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(g_far_mu);
+            g_far_ms += ms;
+            g_far_launches += 1;
+        }
+        if (nq <= qcap)
+            break;
+        // queue overflow: the exact size is now known, run the sweep once more
+        qcap = nq;
+        c->qcap_hint = nq + nq / 4;
+        if (attempt == 1)
+            return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: near-field queue overflow twice");
+    }
+
+    const unsigned long long *d_keys = nullptr;
+    if (nq > 0) {
+        CUDA_TRY(c->keys_sorted.reserve((size_t)nq * sizeof(unsigned long long)));
+        CUDA_TRY(c->pair_result.reserve((size_t)nq * sizeof(double)));
+        int pbits = 1;
+        while (pbits < 32 && (1ll << pbits) < P)
+            pbits++;
+        size_t temp_bytes = 0;
+        CUDA_TRY(tvd_sort_keys(nullptr, temp_bytes, c->queue.as<unsigned long long>(),
+                               c->keys_sorted.as<unsigned long long>(), (int64_t)nq, 32 + pbits,
+                               stream));
+        CUDA_TRY(c->sort_temp.reserve(temp_bytes ? temp_bytes : 16));
+        CUDA_TRY(tvd_sort_keys(c->sort_temp.p, temp_bytes, c->queue.as<unsigned long long>(),
+                               c->keys_sorted.as<unsigned long long>(), (int64_t)nq, 32 + pbits,
+                               stream));
+        d_keys = c->keys_sorted.as<unsigned long long>();
+        NearArgs na;
+        na.field = field;
+        na.n_pairs = (int64_t)nq;
+        na.keys = d_keys;
+        na.lon = d_lon;
+        na.sinlat = d_sinlat;
+        na.coslat = d_coslat;
+        na.radius = d_radius;
+        na.table = c->tab;
+        na.ratio = ratio;
+        na.stack_size = stack_size;
+        na.pair_result = c->pair_result.as<double>();
+        na.counters = d_cnt + 8;
+        na.leaf_counts = d_leaf_counts;
+        na.n_points = P;
+        CUDA_TRY(tvd_launch_near(na, stream));
+    }
+    CUDA_TRY(tvd_launch_combine(P, n_groups, c->far_out.as<double>(), (int64_t)nq, d_keys,
+                                c->pair_result.as<double>(), d_result, stream));
+    unsigned long long h_cnt[16];
+    CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (h_cnt[8 + 4] != 0)
+        return set_error(TVD_ERR_STACK_OVERFLOW, "Tesseroid stack overflow");
+    if (stats) {
+        const int64_t far_pairs = (int64_t)(all_pairs - nq);
+        const int64_t near_nodes = (int64_t)h_cnt[8 + 0], near_leaves = (int64_t)h_cnt[8 + 1];
+        stats[TVD_ST_NODES] = far_pairs + near_nodes;
+        stats[TVD_ST_LEAVES] = far_pairs + near_leaves;
+        stats[TVD_ST_SPLITS] = (int64_t)h_cnt[8 + 2];
+        stats[TVD_ST_TOO_SMALL] = (int64_t)h_cnt[8 + 3];
+        stats[TVD_ST_PIECES] = Q;
+        stats[TVD_ST_NONROOT_NODES] = near_nodes - (int64_t)nq;
+        // h_cnt[8+5] = walked pairs whose root was integrated after all (one root leaf each)
+        stats[TVD_ST_NONROOT_LEAVES] = near_leaves - (int64_t)h_cnt[8 + 5];
+        stats[TVD_ST_NEAR_PAIRS] = (int64_t)nq;
+    }
+    return TVD_OK;
+}
+
+extern "C" int tvd_forward_device(int field, tvd_model *m, int device, int64_t n_points,
+                                  const double *d_lon, const double *d_sinlat,
+                                  const double *d_coslat, const double *d_radius, double ratio,
+                                  int stack_size, int n_groups, double *d_result, int64_t *stats,
+                                  void *stream)
+{
+    g_last_error.clear();
+    if (!m || field < 0 || field >= TVD_NFIELDS || n_points < 0 || !(ratio > 0))
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward_device: bad argument");
+    DeviceCtx *c = nullptr;
+    int rc = get_ctx(m, device, &c);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_TRY(cudaSetDevice(device));
+    return forward_core(m, c, field, n_points, d_lon, d_sinlat, d_coslat, d_radius, ratio,
+                        stack_size, n_groups, d_result, stats, nullptr, (cudaStream_t)stream);
+}
+
+// one device's share of tvd_forward: host slices in, host slice out
+static int forward_host_slice(tvd_model *m, int device, int field, int64_t P, int64_t p0,
+                              int64_t P_total, const double *lon, const double *sinlat,
+                              const double *coslat, const double *radius, double ratio,
+                              int stack_size, int n_groups, double *result, int64_t *stats,
+                              int32_t *leaf_counts)
+{
+    DeviceCtx *c = nullptr;
+    int rc = get_ctx(m, device, &c);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_TRY(cudaSetDevice(device));
+    if (stats)
+        memset(stats, 0, TVD_NSTATS * sizeof(int64_t));
+    if (P == 0)
+        return TVD_OK;
+    CUDA_TRY(c->pts.reserve((size_t)P * 4 * sizeof(double)));
+    CUDA_TRY(c->result.reserve((size_t)P * sizeof(double)));
+    double *d_pts = c->pts.as<double>();
+    const double *src[4] = {lon + p0, sinlat + p0, coslat + p0, radius + p0};
+    for (int k = 0; k < 4; k++)
+        CUDA_TRY(cudaMemcpyAsync(d_pts + (size_t)k * P, src[k], P * sizeof(double),
+                                 cudaMemcpyHostToDevice, c->stream));
+    int32_t *d_counts = nullptr;
+    if (leaf_counts) {
+        CUDA_TRY(c->counts.reserve((size_t)m->n_tess * P * sizeof(int32_t) + 16));
+        d_counts = c->counts.as<int32_t>();
+        CUDA_TRY(tvd_launch_init_counts(c->tab, P, d_counts, c->stream));
+    }
+    rc = forward_core(m, c, field, P, d_pts, d_pts + P, d_pts + 2 * P, d_pts + 3 * P, ratio,
+                      stack_size, n_groups, c->result.as<double>(), stats, d_counts, c->stream);
+    if (rc)
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(result + p0, c->result.p, P * sizeof(double), cudaMemcpyDeviceToHost,
+                             c->stream));
+    if (leaf_counts && m->n_tess > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(leaf_counts + p0, (size_t)P_total * sizeof(int32_t), d_counts,
+                                   (size_t)P * sizeof(int32_t), (size_t)P * sizeof(int32_t),
+                                   (size_t)m->n_tess, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TVD_OK;
+}
+
+extern "C" int tvd_forward(int field, tvd_model *m, int64_t n_points, const double *lon,
+                           const double *sinlat, const double *coslat, const double *radius,
+                           double ratio, int stack_size, int n_devices, const int *device_ids,
+                           double *result, int64_t *stats, int32_t *leaf_counts)
+{
+    g_last_error.clear();
+    if (!m || field < 0 || field >= TVD_NFIELDS || n_points < 0 || !(ratio > 0) || n_devices < 1 ||
+        (n_points > 0 && (!lon || !sinlat || !coslat || !radius || !result)))
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: bad argument");
+    const int ndev_avail = tvd_device_count();
+    if (ndev_avail == 0)
+        return set_error(TVD_ERR_NO_DEVICE, "tvd_forward: no CUDA device (no CPU fallback)");
+    if (stats)
+        memset(stats, 0, TVD_NSTATS * sizeof(int64_t));
+    if (n_points == 0)
+        return TVD_OK;
+    int nparts = n_devices;
+    if ((int64_t)nparts > n_points)
+        nparts = (int)n_points;
+    for (int d = 0; d < nparts; d++) {
+        const int id = device_ids ? device_ids[d] : d;
+        if (id < 0 || id >= ndev_avail)
+            return set_error(TVD_ERR_NO_DEVICE, "tvd_forward: no such CUDA device");
+    }
+    const int n_groups = plan_groups(m->n_pieces, n_points);
+    // _split_arrays (tesseroid.py:318-323): n = size//nparts, the last chunk takes the remainder
+    const int64_t chunk = n_points / nparts;
+    std::vector<int> rcs(nparts, 0);
+    std::vector<std::string> errs(nparts);
+    std::vector<std::vector<int64_t>> st(nparts, std::vector<int64_t>(TVD_NSTATS, 0));
+    auto work = [&](int d) {
+        const int id = device_ids ? device_ids[d] : d;
+        const int64_t p0 = (int64_t)d * chunk;
+        const int64_t p1 = (d == nparts - 1) ? n_points : p0 + chunk;
+        rcs[d] = forward_host_slice(m, id, field, p1 - p0, p0, n_points, lon, sinlat, coslat,
+                                    radius, ratio, stack_size, n_groups, result, st[d].data(),
+                                    leaf_counts);
+        if (rcs[d])
+            errs[d] = g_last_error;
+    };
+    if (nparts == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (int d = 0; d < nparts; d++)
+            threads.emplace_back(work, d);
+        for (auto &t : threads)
+            t.join();
+    }
+    for (int d = 0; d < nparts; d++)
+        if (rcs[d]) {
+            g_last_error = errs[d];
+            return rcs[d];
+        }
+    if (stats) {
+        for (int d = 0; d < nparts; d++)
+            for (int k = 0; k < TVD_NSTATS; k++)
+                stats[k] += st[d][k];
+        stats[TVD_ST_PIECES] = m->n_pieces;
+    }
+    return TVD_OK;
+}

@@ -1,0 +1,367 @@
+// tvd_far.cu -- Phase A: the far-field sweep (the dominant kernel), sm_100a FP64.
+//
+// One thread owns PPT computation points and walks the radial-piece table of its piece group.
+// Piece records are staged through shared memory in TVD_TILE-piece tiles by bulk asynchronous
+// copies (cp.async.bulk, i.e. the TMA 1-D path, completing on an mbarrier; double buffered) and
+// are read as broadcast LDS.128 (all lanes read the same record).  Per (piece, point):
+//
+//   1. conservative far-field test on the squared centre distance (9 FP64 ops, no sqrt, no
+//      libm): if it clears the threshold, the literal test of the reference
+//      (divisions, _tesseroid.pyx:129-146) is guaranteed to say "no split";
+//   2. far pairs: the 2x2x2 GLQ of the root cell (kernel*, _tesseroid.pyx:231-520) with the
+//      point-independent node data precomputed in the record; cos psi and l^2 keep the
+//      reference's operation order and are NOT contracted;
+//   3. every other pair is appended to the near-field queue (warp-aggregated atomic) and is
+//      walked literally by Phase B (tvd_near.cu).
+//
+// The per-point sum over the pieces of a group is sequential in piece order; groups are summed
+// in group order by Phase C, so a point's value does not depend on how points are sharded.
+#include "tvd_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA 1-D)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], "
+                 "%2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 building blocks
+// ---------------------------------------------------------------------------------------------
+// 1/sqrt(x) to ~1 ulp: MUFU.RSQ64H seed (>= 20 bits) + one third-order correction
+//   e = 1 - x*y0^2 ;  y = y0*(1 + e/2 + 3e^2/8)        (error ~ (5/16) e^3 < 2^-60)
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double t = x * y0;
+    const double e = fma(-t, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = e * p;
+    return fma(y0, q, y0);
+}
+
+template <int FIELD>
+struct FieldTraits {
+    static constexpr bool needs_sinlon = (FIELD == TVD_GY || FIELD == TVD_GXY ||
+                                          FIELD == TVD_GYY || FIELD == TVD_GYZ);
+    static constexpr bool needs_kphi = (FIELD == TVD_GX || FIELD == TVD_GXX ||
+                                        FIELD == TVD_GXY || FIELD == TVD_GXZ);
+};
+
+struct PointRegs {
+    double lon, sinlat, coslat, r, r_sqr, r2, cl, sl;
+};
+
+// GLQ of the root cell of one piece for one point.  g = glq record in shared memory.
+template <int FIELD>
+__device__ __forceinline__ double glq_root(const PointRegs &pt, const double *__restrict__ g)
+{
+    const double2 lonc = *reinterpret_cast<const double2 *>(g + 0);
+    const double2 sinlatc = *reinterpret_cast<const double2 *>(g + 2);
+    const double2 coslatc = *reinterpret_cast<const double2 *>(g + 4);
+    const double2 rc = *reinterpret_cast<const double2 *>(g + 6);
+    const double2 rcsq = *reinterpret_cast<const double2 *>(g + 8);
+    const double2 w0 = *reinterpret_cast<const double2 *>(g + 10);   // w[0][0], w[0][1]
+    const double2 w1 = *reinterpret_cast<const double2 *>(g + 12);   // w[1][0], w[1][1]
+
+    double coslon[2], sinlon[2];
+    if (FieldTraits<FIELD>::needs_sinlon) {
+        // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)
+        double s0, s1;
+        sincos(pt.lon - lonc.x, &s0, &coslon[0]);
+        sincos(pt.lon - lonc.y, &s1, &coslon[1]);
+        sinlon[0] = -s0;
+        sinlon[1] = -s1;
+    } else {
+        coslon[0] = cos(pt.lon - lonc.x);
+        coslon[1] = cos(pt.lon - lonc.y);
+        sinlon[0] = sinlon[1] = 0.0;
+    }
+    // reference order: sinlat*sinlatc[j] + coslat*coslatc[j]*coslon   (:244), no contraction
+    const double ss[2] = {pt.sinlat * sinlatc.x, pt.sinlat * sinlatc.y};
+    const double cc[2] = {pt.coslat * coslatc.x, pt.coslat * coslatc.y};
+    // r_sqr + rc_sqr - 2*radius*rc[k]*cospsi   (:247)
+    const double b[2] = {pt.r_sqr + rcsq.x, pt.r_sqr + rcsq.y};
+    const double a[2] = {pt.r2 * rc.x, pt.r2 * rc.y};
+    const double rck[2] = {rc.x, rc.y};
+    const double wjk[2][2] = {{w0.x, w0.y}, {w1.x, w1.y}};
+    const double slc[2] = {sinlatc.x, sinlatc.y};
+    const double clc[2] = {coslatc.x, coslatc.y};
+
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const double cospsi = ss[j] + cc[j] * coslon[i];
+            double kphi = 0.0;
+            if (FieldTraits<FIELD>::needs_kphi)
+                kphi = pt.coslat * slc[j] - pt.sinlat * clc[j] * coslon[i];   // :322
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const double l_sqr = b[k] - a[k] * cospsi;
+                const double y = rsqrt_fast(l_sqr);
+                const double w = wjk[j][k];
+                if (FIELD == TVD_POTENTIAL) {
+                    sum = fma(w, y, sum);                                  // kappa/sqrt(l_sqr)
+                } else {
+                    const double y3 = y * y * y;
+                    if (FIELD == TVD_GX) {
+                        sum = fma(w * kphi, y3, sum);
+                    } else if (FIELD == TVD_GY) {
+                        sum = fma(w * sinlon[i], y3, sum);
+                    } else if (FIELD == TVD_GZ) {
+                        const double dz = rck[k] * cospsi - pt.r;          // :487
+                        sum = fma(w * dz, y3, sum);
+                    } else {
+                        // gradient tensor (Fatiando 0.5 integrands, z up)
+                        const double y5 = y3 * y * y;
+                        const double dx = rck[k] * kphi;
+                        const double dy = rck[k] * clc[j] * sinlon[i];
+                        const double dz = rck[k] * cospsi - pt.r;
+                        double num;
+                        if (FIELD == TVD_GXX) num = 3.0 * (dx * dx) - l_sqr;
+                        else if (FIELD == TVD_GXY) num = 3.0 * dx * dy;
+                        else if (FIELD == TVD_GXZ) num = 3.0 * dx * dz;
+                        else if (FIELD == TVD_GYY) num = 3.0 * (dy * dy) - l_sqr;
+                        else if (FIELD == TVD_GYZ) num = 3.0 * dy * dz;
+                        else num = 3.0 * (dz * dz) - l_sqr;
+                        sum = fma(w * num, y5, sum);
+                    }
+                }
+            }
+        }
+    }
+    return sum;
+}
+
+template <int FIELD, int PPT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+far_sweep(const FarArgs a)
+{
+    __shared__ __align__(16) double s_test[2][TVD_TILE * TVD_TEST_REC];
+    __shared__ __align__(16) double s_glq[2][TVD_TILE * TVD_GLQ_REC];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int g = blockIdx.y;
+    const int64_t q_begin = (int64_t)g * a.pieces_per_group;
+    int64_t q_end = q_begin + a.pieces_per_group;
+    if (q_end > a.n_pieces)
+        q_end = a.n_pieces;
+    const int n_tiles = (int)((q_end - q_begin + TVD_TILE - 1) / TVD_TILE);
+
+    PointRegs pt[PPT];
+    int64_t pidx[PPT];
+    bool valid[PPT];
+    double acc[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+        pidx[u] = (int64_t)blockIdx.x * (THREADS * PPT) + u * THREADS + tid;
+        valid[u] = pidx[u] < a.n_points;
+        const int64_t pi = valid[u] ? pidx[u] : 0;
+        pt[u].lon = a.lon[pi];
+        pt[u].sinlat = a.sinlat[pi];
+        pt[u].coslat = a.coslat[pi];
+        pt[u].r = a.radius[pi];
+        pt[u].r_sqr = pt[u].r * pt[u].r;        // radius**2 (:239)
+        pt[u].r2 = 2.0 * pt[u].r;               // 2*radius  (:247)
+        sincos(pt[u].lon, &pt[u].sl, &pt[u].cl);
+        acc[u] = 0.0;
+    }
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile) {
+        const int st = tile & 1;
+        const int64_t q0 = q_begin + (int64_t)tile * TVD_TILE;
+        int64_t nq = q_end - q0;
+        if (nq > TVD_TILE)
+            nq = TVD_TILE;
+        const uint32_t bt = (uint32_t)(nq * TVD_TEST_REC * sizeof(double));
+        const uint32_t bg = (uint32_t)(nq * TVD_GLQ_REC * sizeof(double));
+        mbar_expect_tx(&s_bar[st], bt + bg);
+        bulk_g2s(s_test[st], a.test_rec + q0 * TVD_TEST_REC, bt, &s_bar[st]);
+        bulk_g2s(s_glq[st], a.glq_rec + q0 * TVD_GLQ_REC, bg, &s_bar[st]);
+    };
+
+    if (tid == 0) {
+        if (n_tiles > 0)
+            issue(0);
+        if (n_tiles > 1)
+            issue(1);
+    }
+
+    for (int tile = 0; tile < n_tiles; tile++) {
+        const int st = tile & 1;
+        mbar_wait(&s_bar[st], (uint32_t)((tile >> 1) & 1));
+        const int64_t q0 = q_begin + (int64_t)tile * TVD_TILE;
+        int nq = (int)((q_end - q0) < TVD_TILE ? (q_end - q0) : TVD_TILE);
+        const double *tt = s_test[st];
+        const double *gg = s_glq[st];
+        for (int qi = 0; qi < nq; qi++) {
+            const double2 t01 = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 0);
+            const double2 t23 = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 2);
+            const double2 t45 = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 4);
+            const double thr2 = tt[qi * TVD_TEST_REC + 6];
+#pragma unroll
+            for (int u = 0; u < PPT; u++) {
+                // conservative squared centre distance (FMA allowed: only the guarded
+                // threshold comparison depends on it)
+                const double coslon_t = fma(pt[u].cl, t01.x, pt[u].sl * t01.y);
+                const double cospsi_t = fma(pt[u].coslat * t23.y, coslon_t, pt[u].sinlat * t23.x);
+                const double d2 = fma(-(pt[u].r * t45.y), cospsi_t, pt[u].r_sqr + t45.x);
+                const bool far = d2 > thr2;
+                const bool defer = valid[u] && !far;
+                const unsigned m = __ballot_sync(0xffffffffu, defer);
+                if (m) {
+                    unsigned long long base = 0;
+                    const int leader = __ffs(m) - 1;
+                    if (lane == leader)
+                        base = atomicAdd(a.qcount, (unsigned long long)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (defer) {
+                        const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
+                        if (idx < a.qcap)
+                            a.queue[idx] = ((unsigned long long)pidx[u] << 32) |
+                                           (unsigned long long)(q0 + qi);
+                    }
+                }
+                if (far)
+                    acc[u] += glq_root<FIELD>(pt[u], gg + qi * TVD_GLQ_REC);
+            }
+        }
+        __syncthreads();    // everyone is done with stage st
+        if (tid == 0 && tile + 2 < n_tiles)
+            issue(tile + 2);
+    }
+
+#pragma unroll
+    for (int u = 0; u < PPT; u++)
+        if (valid[u])
+            a.far_out[(int64_t)g * a.n_points + pidx[u]] = acc[u];
+}
+
+template <int FIELD>
+static cudaError_t launch_field(const FarArgs &a, cudaStream_t stream)
+{
+    constexpr int THREADS = 128, PPT = 1;
+    dim3 grid((unsigned)((a.n_points + THREADS * PPT - 1) / (THREADS * PPT)), (unsigned)a.n_groups);
+    far_sweep<FIELD, PPT, THREADS><<<grid, THREADS, 0, stream>>>(a);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t tvd_launch_far(const FarArgs &a, cudaStream_t stream)
+{
+    if (a.n_points == 0 || a.n_pieces == 0)
+        return cudaSuccess;
+    switch (a.field) {
+    case TVD_POTENTIAL: return launch_field<TVD_POTENTIAL>(a, stream);
+    case TVD_GX: return launch_field<TVD_GX>(a, stream);
+    case TVD_GY: return launch_field<TVD_GY>(a, stream);
+    case TVD_GZ: return launch_field<TVD_GZ>(a, stream);
+    case TVD_GXX: return launch_field<TVD_GXX>(a, stream);
+    case TVD_GXY: return launch_field<TVD_GXY>(a, stream);
+    case TVD_GXZ: return launch_field<TVD_GXZ>(a, stream);
+    case TVD_GYY: return launch_field<TVD_GYY>(a, stream);
+    case TVD_GYZ: return launch_field<TVD_GYZ>(a, stream);
+    case TVD_GZZ: return launch_field<TVD_GZZ>(a, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 peak probe (roofline denominator): 16 independent DFMA chains per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_probe(double *out, int iters, double x, double y)
+{
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        acc[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            acc[i] = fma(acc[i], x, y);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        s += acc[i];
+    if (s == 123.456)
+        out[0] = s;
+}
+
+double tvd_fp64_probe(int iters, cudaStream_t stream)
+{
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double *d_out = nullptr;
+    if (cudaMalloc(&d_out, sizeof(double)) != cudaSuccess)
+        return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = sms * 8, threads = 256;
+    dfma_probe<<<blocks, threads, 0, stream>>>(d_out, 64, 0.999999, 1e-9);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, stream);
+        dfma_probe<<<blocks, threads, 0, stream>>>(d_out, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best)
+            best = tf;
+    }
+    tvd_count_launch(6);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return best;
+}

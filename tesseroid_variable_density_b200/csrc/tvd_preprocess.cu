@@ -1,0 +1,377 @@
+// tvd_preprocess.cu -- point-independent preprocessing kernels (sm_100a).
+//
+// K1  density-based radial discretisation, one thread per tesseroid
+//     (reference: _density_based_discretization / _divider_calculation,
+//      code/tesseroid_density/tesseroid.py:237-300; NumPy semantics restated literally)
+// K4  per-piece root records for the far-field sweep: the point-independent halves of
+//     distance_n_size (_tesseroid.pyx:104-123) and scale_nodes (:152-176), the density at the
+//     radial GLQ nodes (:274) and the field-specific node weights.
+#include "tvd_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------
+// numpy.linspace(start, stop, 101)[i]  (tesseroid.py:258,293): i*step + start, last = stop;
+// a zero step takes NumPy's denormal branch (i/100)*delta + start.
+__device__ __forceinline__ double linspace101(double start, double stop, double delta,
+                                              double step, int i)
+{
+    if (i == 100)
+        return stop;
+    if (step == 0.0)
+        return ((double)i / 100.0) * delta + start;
+    return (double)i * step + start;
+}
+
+// numpy.isclose(a, b), rtol=1e-5, atol=1e-8 (tesseroid.py:262)
+__device__ __forceinline__ bool isclose_default(double a, double b)
+{
+    if (isfinite(a) && isfinite(b))
+        return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b));
+    return a == b;
+}
+
+// tesseroid.py:286-300
+__device__ void divider_calculation(double top, double bottom, int kind, const double *p,
+                                    double rho_min, double rho_max, double &divider,
+                                    double &max_diff)
+{
+    const double delta = top - bottom;
+    const double step = delta / 100.0;
+    const double range = rho_max - rho_min;
+    const double nd0 = (tvd_density(kind, p, bottom) - rho_min) / range;   // heights[0] == start
+    const double nd100 = (tvd_density(kind, p, top) - rho_min) / range;
+    const double slope = (nd100 - nd0) / (top - bottom);
+    double best = -1.0, best_h = bottom;
+    bool has_nan = false;
+    for (int i = 0; i < 101; i++) {
+        const double h = linspace101(bottom, top, delta, step, i);
+        const double nd = (tvd_density(kind, p, h) - rho_min) / range;
+        const double line = slope * (h - bottom) + nd0;
+        const double diff = fabs(nd - line);
+        if (diff != diff) {                 // numpy max/argmax propagate the first NaN
+            if (!has_nan) {
+                has_nan = true;
+                best_h = h;
+            }
+        } else if (!has_nan && diff > best) {
+            best = diff;
+            best_h = h;
+        }
+    }
+    max_diff = has_nan ? nan("") : best;
+    divider = best_h;
+}
+
+// heights[0] of linspace is start only when the multiply-add leaves it untouched:
+// 0*step + start == start always (step finite), so nd0 above is exact.
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128)
+k1_discretize(int64_t n_tess, const double *__restrict__ bounds, const int32_t *__restrict__ kinds,
+              const double *__restrict__ params, double delta, int has_delta,
+              int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
+              double *__restrict__ out_top, double *__restrict__ out_bottom,
+              int32_t *__restrict__ out_parent, int *__restrict__ status)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tess)
+        return;
+    const double top = bounds[6 * t + 4], bottom = bounds[6 * t + 5];
+    const int kind = kinds[t];
+    double p[TVD_NPAR];
+#pragma unroll
+    for (int i = 0; i < TVD_NPAR; i++)
+        p[i] = params[TVD_NPAR * t + i];
+    int64_t base = 0;
+    if (EMIT)
+        base = offsets[t];
+    int nout = 0;
+    bool single = (kind == TVD_DENS_CONST) || !has_delta;   // tesseroid.py:222
+    double rho_min = 0, rho_max = 0;
+    if (!single) {
+        // tesseroid.py:258-264
+        const double d = top - bottom, step = d / 100.0;
+        bool has_nan = false;
+        rho_min = rho_max = tvd_density(kind, p, bottom);
+        for (int i = 0; i < 101; i++) {
+            const double rho = tvd_density(kind, p, linspace101(bottom, top, d, step, i));
+            if (rho != rho)
+                has_nan = true;
+            if (rho < rho_min)
+                rho_min = rho;
+            if (rho > rho_max)
+                rho_max = rho;
+        }
+        if (has_nan)
+            rho_min = rho_max = nan("");
+        single = isclose_default(rho_min, rho_max);
+    }
+    if (single) {
+        if (EMIT) {
+            out_top[base] = top;
+            out_bottom[base] = bottom;
+            out_parent[base] = (int32_t)t;
+        } else {
+            counts[t] = 1;
+        }
+        return;
+    }
+    // FIFO of pending intervals (tesseroid.py:267-282), circular buffer in local memory
+    double qt[TVD_MAX_K1_PIECES], qb[TVD_MAX_K1_PIECES];
+    const double tesseroid_size = top - bottom;
+    int head = 0, npending = 1;
+    qt[0] = top;
+    qb[0] = bottom;
+    while (npending > 0) {
+        const double it = qt[head], ib = qb[head];
+        head = (head + 1) % TVD_MAX_K1_PIECES;
+        npending--;
+        double divider, max_diff;
+        divider_calculation(it, ib, kind, p, rho_min, rho_max, divider, max_diff);
+        const double size_ratio = (it - ib) / tesseroid_size;
+        if (max_diff * size_ratio > delta) {
+            if (npending + 2 + nout > TVD_MAX_K1_PIECES) {
+                atomicExch(status, TVD_ERR_TOO_MANY_PIECES);
+                if (!EMIT)
+                    counts[t] = 0;
+                return;
+            }
+            int tail = (head + npending) % TVD_MAX_K1_PIECES;
+            qt[tail] = it;
+            qb[tail] = divider;
+            tail = (tail + 1) % TVD_MAX_K1_PIECES;
+            qt[tail] = divider;
+            qb[tail] = ib;
+            npending += 2;
+        } else {
+            if (EMIT) {
+                out_top[base + nout] = it;
+                out_bottom[base + nout] = ib;
+                out_parent[base + nout] = (int32_t)t;
+            }
+            nout++;
+        }
+    }
+    if (!EMIT)
+        counts[t] = nout;
+}
+
+cudaError_t tvd_launch_k1_count(const PieceTable &t, double delta, int has_delta, int *d_status,
+                                cudaStream_t stream)
+{
+    if (t.n_tess == 0)
+        return cudaSuccess;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((t.n_tess + threads - 1) / threads);
+    k1_discretize<false><<<blocks, threads, 0, stream>>>(
+        t.n_tess, t.tess_bounds, t.tess_kind, t.tess_params, delta, has_delta, t.tess_npieces,
+        nullptr, nullptr, nullptr, nullptr, d_status);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t tvd_launch_k1_emit(const PieceTable &t, const int64_t *d_offsets, double delta,
+                               int has_delta, cudaStream_t stream)
+{
+    if (t.n_tess == 0)
+        return cudaSuccess;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((t.n_tess + threads - 1) / threads);
+    k1_discretize<true><<<blocks, threads, 0, stream>>>(
+        t.n_tess, t.tess_bounds, t.tess_kind, t.tess_params, delta, has_delta, nullptr, d_offsets,
+        t.top, t.bottom, t.parent, nullptr);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+// Exclusive scan of int32 counts into int64 offsets (offsets[n] = total).  One block walks the
+// array in 1024-element strips carrying the running total: O(n) and launch-latency bound,
+// called once per model.
+__global__ void __launch_bounds__(1024)
+scan_counts(const int32_t *__restrict__ counts, int64_t *__restrict__ offsets, int64_t n)
+{
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0)
+        carry_s = 0;
+    __syncthreads();
+    for (int64_t start = 0; start < n; start += 1024) {
+        const int64_t i = start + threadIdx.x;
+        const int64_t v = i < n ? (int64_t)counts[i] : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o)
+                x += y;
+        }
+        if (lane == 31)
+            warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o)
+                    w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int64_t carry = carry_s;
+        const int64_t incl = x + (warp > 0 ? warp_sums[warp - 1] : 0) + carry;
+        if (i < n)
+            offsets[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        offsets[n] = carry_s;
+}
+
+cudaError_t tvd_launch_scan(const int32_t *d_counts, int64_t *d_offsets, int64_t n,
+                            cudaStream_t stream)
+{
+    scan_counts<<<1, 1024, 0, stream>>>(d_counts, d_offsets, n);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: root records
+// ---------------------------------------------------------------------------------------------
+// test record  [8]: cos(lont) sin(lont) sinlatt coslatt rt^2 2*rt thr2 (pad)
+//   thr2 is the conservative far-field threshold on the squared centre distance, see
+//   tvd_far.cu; pairs that do not clear it are re-examined with the literal test.
+// glq record  [16]: lonc0 lonc1 sinlatc0 sinlatc1 coslatc0 coslatc1 rc0 rc1 rc0^2 rc1^2
+//                   w00 w01 w10 w11 (w[j][k]) (pad) (pad)
+__global__ void __launch_bounds__(128)
+k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bounds,
+              const int32_t *__restrict__ tess_kind, const double *__restrict__ tess_params,
+              const double *__restrict__ ptop, const double *__restrict__ pbottom,
+              const int32_t *__restrict__ parent, double ratio, double *__restrict__ test_rec,
+              double *__restrict__ glq_rec)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pieces)
+        return;
+    const int64_t t = parent[q];
+    const double w = tess_bounds[6 * t + 0], e = tess_bounds[6 * t + 1];
+    const double s = tess_bounds[6 * t + 2], n = tess_bounds[6 * t + 3];
+    const double top = ptop[q], bottom = pbottom[q];
+    const int kind = tess_kind[t];
+    double p[TVD_NPAR];
+#pragma unroll
+    for (int i = 0; i < TVD_NPAR; i++)
+        p[i] = tess_params[TVD_NPAR * t + i];
+
+    // distance_n_size, point-independent part (_tesseroid.pyx:111-122)
+    const double rt = 0.5 * (top + bottom) + TVD_R;
+    const double lont = TVD_D2R * 0.5 * (w + e);
+    const double latt = TVD_D2R * 0.5 * (s + n);
+    const double sinlatt = sin(latt), coslatt = cos(latt);
+    const double rtop = top + TVD_R;
+    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * cos(TVD_D2R * (e - w)));
+    const double Llat = rtop * acos(sin(TVD_D2R * n) * sin(TVD_D2R * s) +
+                                    cos(TVD_D2R * n) * cos(TVD_D2R * s));
+    // Conservative far-field threshold.  The literal test (divisions, :135,140) splits iff
+    // d <= ratio*Llon or d <= ratio*Llat (NaN sizes never split).  The sweep evaluates d^2
+    // with an absolute error far below 1 m^2, so d2 > thr^2*(1+1e-9) + 2 guarantees that the
+    // literal test says "no split"; everything else is deferred to the literal walk.
+    const double thr = fmax(ratio * Llon, ratio * Llat);    // fmax ignores a single NaN
+    const double thr2 = thr * thr * (1.0 + 1e-9) + 2.0;     // NaN if both sizes are NaN
+    double *tr = test_rec + TVD_TEST_REC * q;
+    tr[0] = cos(lont);
+    tr[1] = sin(lont);
+    tr[2] = sinlatt;
+    tr[3] = coslatt;
+    tr[4] = rt * rt;
+    tr[5] = 2.0 * rt;
+    tr[6] = thr2;
+    tr[7] = 0.0;
+
+    // scale_nodes (_tesseroid.pyx:162-175)
+    const double dlon = e - w, dlat = n - s, dr = top - bottom;
+    const double mlon = 0.5 * (e + w), mlat = 0.5 * (n + s);
+    const double mr = 0.5 * (top + bottom + 2. * TVD_R);
+    double lonc[2], sinlatc[2], coslatc[2], rc[2], rcsq[2], dens[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double node = i == 0 ? -TVD_NODE : TVD_NODE;
+        lonc[i] = TVD_D2R * (0.5 * dlon * node + mlon);
+        const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
+        sinlatc[i] = sin(latc);
+        coslatc[i] = cos(latc);
+        rc[i] = (0.5 * dr * node + mr);
+        rcsq[i] = rc[i] * rc[i];
+        dens[i] = tvd_density(kind, p, rc[i] - TVD_R);      // :274 (or the constant, :250)
+    }
+    const double scale = TVD_D2R * dlon * TVD_D2R * dlat * dr * 0.125;
+    double *g = glq_rec + TVD_GLQ_REC * q;
+    g[0] = lonc[0];
+    g[1] = lonc[1];
+    g[2] = sinlatc[0];
+    g[3] = sinlatc[1];
+    g[4] = coslatc[0];
+    g[5] = coslatc[1];
+    g[6] = rc[0];
+    g[7] = rc[1];
+    g[8] = rcsq[0];
+    g[9] = rcsq[1];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double kappa = rcsq[k] * coslatc[j];          // :248
+            double wjk = dens[k] * kappa * scale;
+            switch (field) {
+            case TVD_GX: wjk = wjk * rc[k]; break;                  // kappa*rc*kphi/l^3   (:328)
+            case TVD_GY: wjk = wjk * rc[k] * coslatc[j]; break;     // kappa*rc*coslatc*sinlon/l^3 (:408)
+            case TVD_GZ: wjk = -wjk; break;                         // z down (:490)
+            default: break;
+            }
+            g[10 + 2 * j + k] = wjk;
+        }
+    }
+    g[14] = 0.0;
+    g[15] = 0.0;
+}
+
+cudaError_t tvd_launch_pack(int field, const PieceTable &t, double ratio, double *d_test,
+                            double *d_glq, cudaStream_t stream)
+{
+    if (t.n_pieces == 0)
+        return cudaSuccess;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((t.n_pieces + threads - 1) / threads);
+    k4_pack_roots<<<blocks, threads, 0, stream>>>(field, t.n_pieces, t.tess_bounds, t.tess_kind,
+                                                  t.tess_params, t.top, t.bottom, t.parent, ratio,
+                                                  d_test, d_glq);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void init_counts(int64_t n_tess, int64_t n_points, const int32_t *__restrict__ npieces,
+                            int32_t *__restrict__ counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tess * n_points)
+        counts[i] = npieces[i / n_points];
+}
+
+cudaError_t tvd_launch_init_counts(const PieceTable &t, int64_t n_points, int32_t *counts,
+                                   cudaStream_t stream)
+{
+    const int64_t n = t.n_tess * n_points;
+    if (n == 0)
+        return cudaSuccess;
+    init_counts<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(t.n_tess, n_points,
+                                                                 t.tess_npieces, counts);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
