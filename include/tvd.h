@@ -172,6 +172,11 @@ double tvd_far_kernel_ms(int reset, int64_t *n_launches);
  * FP64 rate in TFLOP/s (FMA = 2 flops).  Roofline denominator, see DESIGN.md. */
 double tvd_measure_fp64_peak(int device, int iters);
 
+/* Debug/test hook: the far-field sweep's own cos/sin of the longitude difference evaluated on
+ * `device` for n host values (tests measure them against glibc, which the reference calls at
+ * _tesseroid.pyx:242,401). */
+int tvd_debug_trig(int device, int64_t n, const double *x, double *cos_out, double *sin_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtvd.so")
+# TVD_LIB_PATH: development knob to load an alternative build of the same library
+LIB_PATH = os.environ.get("TVD_LIB_PATH") or os.path.join(_HERE, "csrc", "libtvd.so")
 
 FIELDS = {"potential": 0, "gx": 1, "gy": 2, "gz": 3, "gxx": 4, "gxy": 5, "gxz": 6, "gyy": 7,
           "gyz": 8, "gzz": 9}
@@ -45,6 +46,7 @@ SIGNATURES = {
     "tvd_launch_count": (C.c_int64, [C.c_int]),
     "tvd_far_kernel_ms": (C.c_double, [C.c_int, _lp]),
     "tvd_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
+    "tvd_debug_trig": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp]),
 }
 
 

@@ -267,6 +267,31 @@ extern "C" double tvd_measure_fp64_peak(int device, int iters)
     return tvd_fp64_probe(iters > 0 ? iters : 4096, nullptr);
 }
 
+extern "C" int tvd_debug_trig(int device, int64_t n, const double *x, double *cos_out,
+                              double *sin_out)
+{
+    g_last_error.clear();
+    if (n < 0 || (n > 0 && (!x || !cos_out || !sin_out)))
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_debug_trig: bad argument");
+    if (tvd_device_count() <= device || device < 0)
+        return set_error(TVD_ERR_NO_DEVICE, "tvd_debug_trig: no such CUDA device");
+    if (n == 0)
+        return TVD_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)n * 3 * sizeof(double)));
+    cudaError_t e = cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = tvd_debug_trig_launch(n, d, d + n, d + 2 * n, nullptr);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(cos_out, d + n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(sin_out, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CUDA_TRY(e);
+    return TVD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ABI: model
 // ---------------------------------------------------------------------------------------------
@@ -410,10 +435,11 @@ static int plan_groups(int64_t n_pieces, int64_t n_points_total)
 {
     // Enough thread blocks for ~2 waves of 4 resident 128-thread blocks on 148 SMs, but never
     // groups smaller than 4 tiles.  Pure function of (Q, P_total).
-    const int64_t blocks_x = (n_points_total + 127) / 128;
+    const int64_t ppb = (int64_t)TVD_FAR_THREADS * TVD_FAR_PPT;
+    const int64_t blocks_x = (n_points_total + ppb - 1) / ppb;
     if (blocks_x <= 0 || n_pieces <= 0)
         return 1;
-    const int64_t want = 148 * 4 * 2;
+    const int64_t want = 148 * TVD_FAR_MINBLOCKS * 2;
     int64_t g = (want + blocks_x - 1) / blocks_x;
     const int64_t gmax = n_pieces / (4 * TVD_TILE);
     if (g > gmax)

@@ -74,6 +74,126 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     return fma(y0, q, y0);
 }
 
+// ---------------------------------------------------------------------------------------------
+// cos / sincos of the longitude difference.
+//
+// libdevice's cos() costs ~20 FP64 + ~25 integer/branch/table-load instructions (special-case
+// tests, a Payne-Hanek slow path, coefficients fetched from a global table).  The sweep only
+// needs |x| up to a few pi, so it carries its own: Cody-Waite reduction by pi/2 (33-bit head, so
+// k*head is exact) keeping the reduction tail, then the fdlibm kernels (error < 1 ulp; for the
+// small arguments of regional models the result is correctly rounded in almost every case,
+// i.e. it agrees with glibc's cos, which the reference calls).  When every lane of the warp
+// has |x| <= pi/4 (regional models) no reduction is done at all.
+// ---------------------------------------------------------------------------------------------
+#define TVD_PIO4 0.78539816339744830962
+__device__ __forceinline__ double kcos(double x, double y)
+{
+    const double z = x * x;
+    double r = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    r = fma(z, r, -2.75573143513906633035e-07);
+    r = fma(z, r, 2.48015872894767294178e-05);
+    r = fma(z, r, -1.38888888888741095749e-03);
+    r = fma(z, r, 4.16666666666666019037e-02);
+    r = r * z;
+    const double hz = 0.5 * z;
+    const double w = 1.0 - hz;
+    return w + (((1.0 - w) - hz) + fma(z, r, -(x * y)));
+}
+__device__ __forceinline__ double kcos0(double x)      // tail y == 0
+{
+    const double z = x * x;
+    double r = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    r = fma(z, r, -2.75573143513906633035e-07);
+    r = fma(z, r, 2.48015872894767294178e-05);
+    r = fma(z, r, -1.38888888888741095749e-03);
+    r = fma(z, r, 4.16666666666666019037e-02);
+    r = r * z;
+    const double hz = 0.5 * z;
+    const double w = 1.0 - hz;
+    return w + fma(z, r, (1.0 - w) - hz);
+}
+__device__ __forceinline__ double ksin(double x, double y)
+{
+    const double z = x * x;
+    const double v = z * x;
+    double r = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    r = fma(z, r, 2.75573137070700676789e-06);
+    r = fma(z, r, -1.98412698298579493134e-04);
+    r = fma(z, r, 8.33333333332248946124e-03);
+    // x - ((z*(0.5*y - v*r) - y) - v*S1)
+    return x - ((z * fma(-v, r, 0.5 * y) - y) - v * -1.66666666666666324348e-01);
+}
+__device__ __forceinline__ double ksin0(double x)
+{
+    const double z = x * x;
+    const double v = z * x;
+    double r = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    r = fma(z, r, 2.75573137070700676789e-06);
+    r = fma(z, r, -1.98412698298579493134e-04);
+    r = fma(z, r, 8.33333333332248946124e-03);
+    r = fma(z, r, -1.66666666666666324348e-01);
+    return fma(v, r, x);
+}
+// general argument: returns quadrant, reduced argument r and its tail y (x = k*pi/2 + r + y)
+__device__ __forceinline__ int reduce_pio2(double x, double &r, double &y)
+{
+    const double t = fma(x, 6.36619772367581382433e-01, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    const double r0 = fma(-kd, 1.57079632673412561417e+00, x);    // exact
+    const double w = kd * 6.07710050650619224932e-11;
+    r = r0 - w;
+    y = (r0 - r) - w;
+    return k;
+}
+// cos (and, if WANT_SIN, sin) of two arguments.  Warp-uniform fast path for |x| <= pi/4.
+template <bool WANT_SIN>
+__device__ __forceinline__ void trig2(double x0, double x1, double &c0, double &c1, double &s0,
+                                      double &s1)
+{
+    const bool small = fmax(fabs(x0), fabs(x1)) <= TVD_PIO4;
+    if (__all_sync(0xffffffffu, small)) {
+        c0 = kcos0(x0);
+        c1 = kcos0(x1);
+        if (WANT_SIN) {
+            s0 = ksin0(x0);
+            s1 = ksin0(x1);
+        }
+        return;
+    }
+    const bool huge = !(fmax(fabs(x0), fabs(x1)) < 1.0e5);      // also catches NaN/inf
+    if (__any_sync(0xffffffffu, huge)) {
+        if (WANT_SIN) {
+            sincos(x0, &s0, &c0);
+            sincos(x1, &s1, &c1);
+        } else {
+            c0 = cos(x0);
+            c1 = cos(x1);
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double r, y;
+        const int k = reduce_pio2(i == 0 ? x0 : x1, r, y);
+        const double cr = kcos(r, y), sr = ksin(r, y);
+        // cos(x): k&3 = 0: cr, 1: -sr, 2: -cr, 3: sr ;  sin(x): 0: sr, 1: cr, 2: -sr, 3: -cr
+        double c = (k & 1) ? sr : cr;
+        if ((k + 1) & 2)
+            c = -c;
+        double sn = (k & 1) ? cr : sr;
+        if (k & 2)
+            sn = -sn;
+        if (i == 0) {
+            c0 = c;
+            s0 = sn;
+        } else {
+            c1 = c;
+            s1 = sn;
+        }
+    }
+}
+
 template <int FIELD>
 struct FieldTraits {
     static constexpr bool needs_sinlon = (FIELD == TVD_GY || FIELD == TVD_GXY ||
@@ -99,17 +219,13 @@ __device__ __forceinline__ double glq_root(const PointRegs &pt, const double *__
     const double2 w1 = *reinterpret_cast<const double2 *>(g + 12);   // w[1][0], w[1][1]
 
     double coslon[2], sinlon[2];
-    if (FieldTraits<FIELD>::needs_sinlon) {
-        // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)
-        double s0, s1;
-        sincos(pt.lon - lonc.x, &s0, &coslon[0]);
-        sincos(pt.lon - lonc.y, &s1, &coslon[1]);
+    {
+        // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
+        double s0 = 0.0, s1 = 0.0;
+        trig2<FieldTraits<FIELD>::needs_sinlon>(pt.lon - lonc.x, pt.lon - lonc.y, coslon[0],
+                                                coslon[1], s0, s1);
         sinlon[0] = -s0;
         sinlon[1] = -s1;
-    } else {
-        coslon[0] = cos(pt.lon - lonc.x);
-        coslon[1] = cos(pt.lon - lonc.y);
-        sinlon[0] = sinlon[1] = 0.0;
     }
     // reference order: sinlat*sinlatc[j] + coslat*coslatc[j]*coslon   (:244), no contraction
     const double ss[2] = {pt.sinlat * sinlatc.x, pt.sinlat * sinlatc.y};
@@ -169,8 +285,8 @@ __device__ __forceinline__ double glq_root(const PointRegs &pt, const double *__
     return sum;
 }
 
-template <int FIELD, int PPT, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+template <int FIELD, int PPT, int THREADS, int MINBLOCKS>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
 far_sweep(const FarArgs a)
 {
     __shared__ __align__(16) double s_test[2][TVD_TILE * TVD_TEST_REC];
@@ -202,6 +318,10 @@ far_sweep(const FarArgs a)
         pt[u].r_sqr = pt[u].r * pt[u].r;        // radius**2 (:239)
         pt[u].r2 = 2.0 * pt[u].r;               // 2*radius  (:247)
         sincos(pt[u].lon, &pt[u].sl, &pt[u].cl);
+        // padding threads: an infinite r^2 makes every pair "far", so they never touch the
+        // near-field queue; their sums are garbage and are never stored
+        if (!valid[u])
+            pt[u].r_sqr = __longlong_as_double(0x7ff0000000000000ll);
         acc[u] = 0.0;
     }
 
@@ -252,7 +372,7 @@ far_sweep(const FarArgs a)
                 const double cospsi_t = fma(pt[u].coslat * t23.y, coslon_t, pt[u].sinlat * t23.x);
                 const double d2 = fma(-(pt[u].r * t45.y), cospsi_t, pt[u].r_sqr + t45.x);
                 const bool far = d2 > thr2;
-                const bool defer = valid[u] && !far;
+                const bool defer = !far;
                 const unsigned m = __ballot_sync(0xffffffffu, defer);
                 if (m) {
                     unsigned long long base = 0;
@@ -267,8 +387,11 @@ far_sweep(const FarArgs a)
                                            (unsigned long long)(q0 + qi);
                     }
                 }
+                // every lane evaluates the root GLQ (it contains warp-wide votes); lanes whose
+                // pair was deferred simply drop the value
+                const double v = glq_root<FIELD>(pt[u], gg + qi * TVD_GLQ_REC);
                 if (far)
-                    acc[u] += glq_root<FIELD>(pt[u], gg + qi * TVD_GLQ_REC);
+                    acc[u] += v;
             }
         }
         __syncthreads();    // everyone is done with stage st
@@ -285,9 +408,9 @@ far_sweep(const FarArgs a)
 template <int FIELD>
 static cudaError_t launch_field(const FarArgs &a, cudaStream_t stream)
 {
-    constexpr int THREADS = 128, PPT = 1;
+    constexpr int THREADS = TVD_FAR_THREADS, PPT = TVD_FAR_PPT;
     dim3 grid((unsigned)((a.n_points + THREADS * PPT - 1) / (THREADS * PPT)), (unsigned)a.n_groups);
-    far_sweep<FIELD, PPT, THREADS><<<grid, THREADS, 0, stream>>>(a);
+    far_sweep<FIELD, PPT, THREADS, TVD_FAR_MINBLOCKS><<<grid, THREADS, 0, stream>>>(a);
     tvd_count_launch();
     return cudaGetLastError();
 }
@@ -364,4 +487,30 @@ double tvd_fp64_probe(int iters, cudaStream_t stream)
     cudaEventDestroy(e1);
     cudaFree(d_out);
     return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug: the sweep's own cos/sin, exposed so that tests can measure them against glibc
+// ---------------------------------------------------------------------------------------------
+__global__ void debug_trig_kernel(int64_t n, const double *__restrict__ x, double *__restrict__ c,
+                                  double *__restrict__ s)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double xi = x[i < n ? i : n - 1];
+    double c0, c1, s0, s1;
+    trig2<true>(xi, xi, c0, c1, s0, s1);
+    if (i < n) {
+        c[i] = c0;
+        s[i] = s0;
+    }
+}
+
+cudaError_t tvd_debug_trig_launch(int64_t n, const double *d_x, double *d_c, double *d_s,
+                                  cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    debug_trig_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, d_x, d_c, d_s);
+    tvd_count_launch();
+    return cudaGetLastError();
 }

@@ -18,6 +18,16 @@
 #define TVD_TEST_REC 8
 #define TVD_GLQ_REC 16
 #define TVD_TILE 64                         // pieces per shared-memory tile
+// far-field sweep launch shape: threads per block, points per thread, resident blocks per SM
+#ifndef TVD_FAR_THREADS
+#define TVD_FAR_THREADS 256
+#endif
+#ifndef TVD_FAR_PPT
+#define TVD_FAR_PPT 1
+#endif
+#ifndef TVD_FAR_MINBLOCKS
+#define TVD_FAR_MINBLOCKS 2
+#endif
 #define TVD_MAX_K1_PIECES 256               // cap on radial pieces of ONE tesseroid
 #define TVD_MAX_DEPTH 64                    // levels of the near-field subdivision stack
 
@@ -104,5 +114,7 @@ cudaError_t tvd_launch_combine(int64_t n_points, int n_groups, const double *far
 cudaError_t tvd_launch_init_counts(const PieceTable &t, int64_t n_points, int32_t *counts,
                                    cudaStream_t stream);
 double tvd_fp64_probe(int iters, cudaStream_t stream);
+cudaError_t tvd_debug_trig_launch(int64_t n, const double *d_x, double *d_c, double *d_s,
+                                  cudaStream_t stream);
 
 void tvd_count_launch(int n = 1);
