@@ -1,0 +1,175 @@
+"""The drop-in Python surface on the GPU: same behaviour as tesseroid_density.tesseroid."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+from tesseroid_variable_density_b200 import density as D
+from tesseroid_variable_density_b200 import gridder, tesseroid, _lib
+from tesseroid_variable_density_b200.mesher import Tesseroid, TesseroidMesh
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("field", cases.ALL_FIELDS)
+def test_analytical_shell_all_ten_fields(field):
+    """<= 0.1 % of the analytical shell at the paper's defaults (manuscript.tex:816-820);
+    components that vanish by symmetry are compared with the scale of gz / gzz."""
+    mesh, _, exact = cases.exponential_case(1e4, 10)
+    lats, lons, heights = cases.GRIDS["260km"]()
+    got = getattr(tesseroid, field)(lons, lats, heights, mesh, delta=0.1)
+    ex = exact(heights[0])
+    want = ex[field]
+    if want != 0:
+        assert cases.percent_difference(got, want) <= 0.1
+    else:
+        scale = abs(ex["gz"]) if field in ("gx", "gy") else abs(ex["gzz"])
+        assert np.max(np.abs(got)) <= 1e-3 * scale
+
+
+@pytest.mark.parametrize("case", ["linear", "exponential", "sine"])
+@pytest.mark.parametrize("grid", ["global2km", "pole2km", "equator2km"])
+def test_analytical_shell_at_2km(case, grid):
+    # BASELINE config 1: gz + potential at 2 km height vs the analytical solution
+    if case == "linear":
+        mesh, _, exact = cases.linear_case(1e4)
+        delta = None
+    elif case == "exponential":
+        mesh, _, exact = cases.exponential_case(1e4, 5)
+        delta = 0.1
+    else:
+        mesh, _, exact = cases.sine_case(1e4, 2)
+        delta = 0.1
+    lats, lons, heights = cases.GRIDS[grid]()
+    ex = exact(heights[0])
+    for field in ("potential", "gz"):
+        got = getattr(tesseroid, field)(lons, lats, heights, mesh, delta=delta)
+        assert cases.percent_difference(got, ex[field]) <= 0.1
+
+
+def test_density_based_discretization_contract():
+    # same return contract as tesseroid.py:237-283: list of [w, e, s, n, top, bottom] arrays
+    A = 1 / (1 - np.exp(-5))
+    dens = D.ExponentialDensity(A, -5, -1000., 1000., 1 - A)
+    subset = tesseroid._density_based_discretization([-10, 10, -10, 10, 0, -1000], dens, 0.1)
+    assert [list(np.round(s, 6)) for s in subset] == [[-10, 10, -10, 10, 0, -680],
+                                                      [-10, 10, -10, 10, -680, -1000]]
+    sine = D.SineDensity(0.5, 2 * np.pi * 2 / 1000., 0.5)
+    subset = tesseroid._density_based_discretization([-10, 10, -10, 10, 0, -1000], sine, 0.1)
+    assert len(subset) == 5
+    # FIFO emission order, not depth order
+    assert round(subset[0][4], 1) == -384.3 and round(subset[3][4], 1) == 0.0
+    lin = D.LinearDensity(-0.01, 0., 0.)
+    assert len(tesseroid._density_based_discretization([-10, 10, -10, 10, 0, -1000], lin, 1e-4)) == 1
+
+
+def test_k1_matches_oracle_on_many_tesseroids(oracle_lib):
+    rng = np.random.default_rng(5)
+    n = 500
+    tops = rng.uniform(-1000, 2000, n)
+    bots = tops - rng.uniform(0, 60000, n)
+    bots[::50] = tops[::50]                   # degenerate cells
+    bounds = np.zeros((n, 6))
+    bounds[:, 1] = 1
+    bounds[:, 3] = 1
+    bounds[:, 4], bounds[:, 5] = tops, bots
+    kinds = rng.integers(0, 4, n).astype(np.int32)
+    params = np.zeros((n, 5))
+    for i in range(n):
+        if kinds[i] == D.CONST:
+            params[i, 0] = 2670
+        elif kinds[i] == D.LINEAR:
+            params[i, :3] = (-0.01, 6378137.0, 60000.)
+        elif kinds[i] == D.EXP:
+            params[i] = (600., -rng.integers(1, 60), bots[i], max(tops[i] - bots[i], 1.0), 2600.)
+        else:
+            params[i, :3] = (1650., 2 * np.pi * rng.integers(1, 6) / max(tops[i] - bots[i], 1.0), 1650.)
+    from tesseroid_variable_density_b200.model import FlatModel
+    for delta in (0.1, 1e-2, 1e-3):
+        pm = tesseroid.PreparedModel(FlatModel(bounds, kinds, params), delta=delta)
+        t, b, parent = pm.pieces()
+        pm.close()
+        pos = 0
+        for i in range(n):
+            if kinds[i] == D.CONST:
+                ot, ob = np.array([tops[i]]), np.array([bots[i]])
+            else:
+                ot, ob = oracle_lib.density_discretize(tops[i], bots[i], kinds[i], params[i], delta)
+            k = len(ot)
+            assert np.array_equal(parent[pos:pos + k], np.full(k, i))
+            assert np.array_equal(t[pos:pos + k], ot) and np.array_equal(b[pos:pos + k], ob), (i, delta)
+            pos += k
+        assert pos == t.size
+
+
+def test_njobs_dens_delta_none_and_shapes(oracle_lib):
+    mesh, dens, _ = cases.exponential_case(1e4, 5)
+    lats, lons, heights = cases.GRIDS["global2km"]()
+    base = tesseroid.gz(lons, lats, heights, mesh, delta=0.1)
+    # njobs maps to the number of GPUs; values do not depend on it (tesseroid.py:179-195)
+    again = tesseroid.gz(lons, lats, heights, mesh, delta=0.1, njobs=4)
+    assert np.array_equal(base, again)
+    # 2-D input arrays keep their shape (zeros_like(lon), tesseroid.py:121)
+    shaped = tesseroid.gz(lons.reshape(19, 13), lats.reshape(19, 13), heights.reshape(19, 13), mesh, delta=0.1)
+    assert shaped.shape == (19, 13) and np.array_equal(shaped.ravel(), base)
+    # dens overrides the model's density (tesseroid.py:157-158)
+    c1 = tesseroid.gz(lons, lats, heights, mesh, dens=1000.)
+    c2 = tesseroid.gz(lons, lats, heights, mesh, dens=2000.)
+    assert np.allclose(c2, 2 * c1, rtol=1e-13)
+    # delta=None disables the radial splitting (tesseroid.py:222)
+    pm = tesseroid.PreparedModel(mesh, delta=None)
+    assert pm.n_pieces == mesh.size
+    pm.close()
+    pm = tesseroid.PreparedModel(mesh, delta=0.1)
+    assert pm.n_pieces == 2 * mesh.size
+    one = tesseroid.gz(lons, lats, heights, pm)         # a prepared model is accepted as `model`
+    assert np.array_equal(one, base)
+    pm.close()
+    with pytest.raises(AssertionError):
+        tesseroid.gz(lons, lats[:-1], heights, mesh)
+    with pytest.raises(AssertionError):
+        tesseroid.gz(lons, lats, heights, mesh, ratio=0)
+    with pytest.raises(TypeError):
+        tesseroid.gz(lons, lats, heights, mesh, dens=lambda h: 1.0)
+
+
+def test_empty_inputs():
+    mesh, _, _ = cases.exponential_case(1e4, 5)
+    empty = np.zeros(0)
+    assert tesseroid.gz(empty, empty, empty, mesh).shape == (0,)
+    lats, lons, heights = cases.GRIDS["pole2km"]()
+    assert np.all(tesseroid.gz(lons, lats, heights, []) == 0)
+    assert np.all(tesseroid.potential(lons, lats, heights, [None, Tesseroid(0, 1, 0, 1, 0, -1)]) == 0)
+
+
+def test_too_small_warning_and_stack_overflow(monkeypatch):
+    # a point inside a microscopic cell: the reference stops dividing below 0.1 m and warns
+    # (tesseroid.py:212-216; _tesseroid.pyx:136-137)
+    cell = [Tesseroid(0, 1e-7, 0, 1e-7, 0, -1e-3, props={"density": 1000.})]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        tesseroid.gz(np.array([5e-8]), np.array([5e-8]), np.array([1e-4]), cell)
+    assert any(issubclass(x.category, RuntimeWarning) and "Stopped dividing" in str(x.message) for x in w)
+    # stack overflow -> ValueError (_tesseroid.pyx:88-89)
+    monkeypatch.setattr(tesseroid, "STACK_SIZE", 3)
+    big = [Tesseroid(-10, 10, -10, 10, 0, -1000, props={"density": 1000.})]
+    with pytest.raises(ValueError, match="Tesseroid stack overflow"):
+        tesseroid.gz(np.array([0.]), np.array([0.]), np.array([10.]), big)
+
+
+def test_own_trig_against_glibc():
+    """The sweep's cos/sin vs math.cos/math.sin (glibc, what the reference calls): <= 1 ulp and
+    equal in >= 95 % of cases; >= 98 % for the small arguments of regional models."""
+    import math
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for lim, frac in ((0.35, 0.98), (0.785, 0.95), (7.0, 0.95), (1000.0, 0.95)):
+        x = rng.uniform(-lim, lim, 100000)
+        c, s = np.empty_like(x), np.empty_like(x)
+        assert lib.tvd_debug_trig(0, x.size, _lib.ptr_f64(x), _lib.ptr_f64(c), _lib.ptr_f64(s)) == 0
+        cref = np.array([math.cos(v) for v in x])
+        sref = np.array([math.sin(v) for v in x])
+        assert np.max(np.abs(c - cref) / np.spacing(np.abs(cref))) <= 1.0
+        assert np.max(np.abs(s - sref) / np.spacing(np.abs(sref))) <= 1.0
+        assert np.mean(c == cref) >= frac and np.mean(s == sref) >= frac
