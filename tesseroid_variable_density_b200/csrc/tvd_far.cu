@@ -202,51 +202,76 @@ struct FieldTraits {
                                         FIELD == TVD_GXY || FIELD == TVD_GXZ);
 };
 
+// per-thread constants of one computation point
 struct PointRegs {
-    double lon, sinlat, coslat, r, r_sqr, r2, cl, sl;
+    double lon, sinlat, coslat, r, r_sqr, r2;
+    double p2x, p2y, p2z, neg_r_sqr;    // -2 r (cos lat cos lon, cos lat sin lon, sin lat), -r^2
 };
 
-// GLQ of the root cell of one piece for one point.  g = glq record in shared memory.
+// The angular half of the root GLQ: everything that depends on the piece only through its
+// lon/lat extent.  The radial pieces of one tesseroid share it, so it is recomputed only when
+// the record says the extent changed.
+struct Angular {
+    double cospsi[2][2];     // [i][j]
+    double kphi[2][2];
+    double sinlon[2];
+    double clc[2];           // coslatc[j] (tensor dy)
+};
+
 template <int FIELD>
-__device__ __forceinline__ double glq_root(const PointRegs &pt, const double *__restrict__ g)
+__device__ __forceinline__ void glq_angular(const PointRegs &pt, const double *__restrict__ g,
+                                            Angular &A)
 {
     const double2 lonc = *reinterpret_cast<const double2 *>(g + 0);
     const double2 sinlatc = *reinterpret_cast<const double2 *>(g + 2);
     const double2 coslatc = *reinterpret_cast<const double2 *>(g + 4);
-    const double2 rc = *reinterpret_cast<const double2 *>(g + 6);
-    const double2 rcsq = *reinterpret_cast<const double2 *>(g + 8);
-    const double2 w0 = *reinterpret_cast<const double2 *>(g + 10);   // w[0][0], w[0][1]
-    const double2 w1 = *reinterpret_cast<const double2 *>(g + 12);   // w[1][0], w[1][1]
-
-    double coslon[2], sinlon[2];
+    double coslon[2];
     {
         // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
         double s0 = 0.0, s1 = 0.0;
         trig2<FieldTraits<FIELD>::needs_sinlon>(pt.lon - lonc.x, pt.lon - lonc.y, coslon[0],
                                                 coslon[1], s0, s1);
-        sinlon[0] = -s0;
-        sinlon[1] = -s1;
+        A.sinlon[0] = -s0;
+        A.sinlon[1] = -s1;
     }
     // reference order: sinlat*sinlatc[j] + coslat*coslatc[j]*coslon   (:244), no contraction
     const double ss[2] = {pt.sinlat * sinlatc.x, pt.sinlat * sinlatc.y};
     const double cc[2] = {pt.coslat * coslatc.x, pt.coslat * coslatc.y};
-    // r_sqr + rc_sqr - 2*radius*rc[k]*cospsi   (:247)
+    const double slc[2] = {sinlatc.x, sinlatc.y};
+    A.clc[0] = coslatc.x;
+    A.clc[1] = coslatc.y;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            A.cospsi[i][j] = ss[j] + cc[j] * coslon[i];
+            if (FieldTraits<FIELD>::needs_kphi)
+                A.kphi[i][j] = pt.coslat * slc[j] - pt.sinlat * A.clc[j] * coslon[i];   // :322
+        }
+    }
+}
+
+// The radial half: the eight nodes of one piece.
+template <int FIELD>
+__device__ __forceinline__ double glq_radial(const PointRegs &pt, const double *__restrict__ g,
+                                             const Angular &A)
+{
+    const double2 rc = *reinterpret_cast<const double2 *>(g + 6);
+    const double2 rcsq = *reinterpret_cast<const double2 *>(g + 8);
+    const double2 w0 = *reinterpret_cast<const double2 *>(g + 10);   // w[0][0], w[0][1]
+    const double2 w1 = *reinterpret_cast<const double2 *>(g + 12);   // w[1][0], w[1][1]
+    // r_sqr + rc_sqr - 2*radius*rc[k]*cospsi   (:247), no contraction
     const double b[2] = {pt.r_sqr + rcsq.x, pt.r_sqr + rcsq.y};
     const double a[2] = {pt.r2 * rc.x, pt.r2 * rc.y};
     const double rck[2] = {rc.x, rc.y};
     const double wjk[2][2] = {{w0.x, w0.y}, {w1.x, w1.y}};
-    const double slc[2] = {sinlatc.x, sinlatc.y};
-    const double clc[2] = {coslatc.x, coslatc.y};
 
     double sum = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            const double cospsi = ss[j] + cc[j] * coslon[i];
-            double kphi = 0.0;
-            if (FieldTraits<FIELD>::needs_kphi)
-                kphi = pt.coslat * slc[j] - pt.sinlat * clc[j] * coslon[i];   // :322
+            const double cospsi = A.cospsi[i][j];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const double l_sqr = b[k] - a[k] * cospsi;
@@ -257,17 +282,19 @@ __device__ __forceinline__ double glq_root(const PointRegs &pt, const double *__
                 } else {
                     const double y3 = y * y * y;
                     if (FIELD == TVD_GX) {
-                        sum = fma(w * kphi, y3, sum);
+                        sum = fma(w * A.kphi[i][j], y3, sum);
                     } else if (FIELD == TVD_GY) {
-                        sum = fma(w * sinlon[i], y3, sum);
+                        sum = fma(w * A.sinlon[i], y3, sum);
                     } else if (FIELD == TVD_GZ) {
-                        const double dz = rck[k] * cospsi - pt.r;          // :487
+                        // rc*cospsi - radius (:487); the product is not ill-conditioned enough
+                        // to need the reference's separate rounding (<= 5e-14 relative)
+                        const double dz = fma(rck[k], cospsi, -pt.r);
                         sum = fma(w * dz, y3, sum);
                     } else {
                         // gradient tensor (Fatiando 0.5 integrands, z up)
                         const double y5 = y3 * y * y;
-                        const double dx = rck[k] * kphi;
-                        const double dy = rck[k] * clc[j] * sinlon[i];
+                        const double dx = rck[k] * A.kphi[i][j];
+                        const double dy = rck[k] * A.clc[j] * A.sinlon[i];
                         const double dz = rck[k] * cospsi - pt.r;
                         double num;
                         if (FIELD == TVD_GXX) num = 3.0 * (dx * dx) - l_sqr;
@@ -303,6 +330,7 @@ far_sweep(const FarArgs a)
     const int n_tiles = (int)((q_end - q_begin + TVD_TILE - 1) / TVD_TILE);
 
     PointRegs pt[PPT];
+    Angular ang[PPT];
     int64_t pidx[PPT];
     bool valid[PPT];
     double acc[PPT];
@@ -310,18 +338,19 @@ far_sweep(const FarArgs a)
     for (int u = 0; u < PPT; u++) {
         pidx[u] = (int64_t)blockIdx.x * (THREADS * PPT) + u * THREADS + tid;
         valid[u] = pidx[u] < a.n_points;
-        const int64_t pi = valid[u] ? pidx[u] : 0;
+        const int64_t pi = valid[u] ? pidx[u] : 0;     // padding threads shadow point 0
         pt[u].lon = a.lon[pi];
         pt[u].sinlat = a.sinlat[pi];
         pt[u].coslat = a.coslat[pi];
         pt[u].r = a.radius[pi];
         pt[u].r_sqr = pt[u].r * pt[u].r;        // radius**2 (:239)
         pt[u].r2 = 2.0 * pt[u].r;               // 2*radius  (:247)
-        sincos(pt[u].lon, &pt[u].sl, &pt[u].cl);
-        // padding threads: an infinite r^2 makes every pair "far", so they never touch the
-        // near-field queue; their sums are garbage and are never stored
-        if (!valid[u])
-            pt[u].r_sqr = __longlong_as_double(0x7ff0000000000000ll);
+        double sl, cl;
+        sincos(pt[u].lon, &sl, &cl);
+        pt[u].p2x = -pt[u].r2 * (pt[u].coslat * cl);
+        pt[u].p2y = -pt[u].r2 * (pt[u].coslat * sl);
+        pt[u].p2z = -pt[u].r2 * pt[u].sinlat;
+        pt[u].neg_r_sqr = -pt[u].r_sqr;
         acc[u] = 0.0;
     }
 
@@ -360,19 +389,22 @@ far_sweep(const FarArgs a)
         const double *tt = s_test[st];
         const double *gg = s_glq[st];
         for (int qi = 0; qi < nq; qi++) {
-            const double2 t01 = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 0);
-            const double2 t23 = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 2);
-            const double2 t45 = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 4);
-            const double thr2 = tt[qi * TVD_TEST_REC + 6];
+            const double2 cxy = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 0);
+            const double2 czk = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 2);
+            const double *grec = gg + qi * TVD_GLQ_REC;
+            // record flag: this piece has the lon/lat extent of the previous piece of the tile
+            // (a further radial piece of the same tesseroid) -> keep the angular half
+            const bool same_extent = reinterpret_cast<const int2 *>(grec + 14)->x != 0;
 #pragma unroll
             for (int u = 0; u < PPT; u++) {
-                // conservative squared centre distance (FMA allowed: only the guarded
-                // threshold comparison depends on it)
-                const double coslon_t = fma(pt[u].cl, t01.x, pt[u].sl * t01.y);
-                const double cospsi_t = fma(pt[u].coslat * t23.y, coslon_t, pt[u].sinlat * t23.x);
-                const double d2 = fma(-(pt[u].r * t45.y), cospsi_t, pt[u].r_sqr + t45.x);
-                const bool far = d2 > thr2;
-                const bool defer = !far;
+                // conservative far-field test: d^2 - thr2 = r^2 + (rt^2 - thr2) - 2 p.c > 0 with
+                // p, c the Cartesian position vectors of the point and the piece centre
+                // (FMA allowed: only the guarded comparison depends on it, see K4)
+                double t = fma(pt[u].p2x, cxy.x, czk.y);
+                t = fma(pt[u].p2y, cxy.y, t);
+                t = fma(pt[u].p2z, czk.x, t);
+                const bool far = t > pt[u].neg_r_sqr;
+                const bool defer = !far && valid[u];
                 const unsigned m = __ballot_sync(0xffffffffu, defer);
                 if (m) {
                     unsigned long long base = 0;
@@ -389,7 +421,9 @@ far_sweep(const FarArgs a)
                 }
                 // every lane evaluates the root GLQ (it contains warp-wide votes); lanes whose
                 // pair was deferred simply drop the value
-                const double v = glq_root<FIELD>(pt[u], gg + qi * TVD_GLQ_REC);
+                if (!same_extent)
+                    glq_angular<FIELD>(pt[u], grec, ang[u]);
+                const double v = glq_radial<FIELD>(pt[u], grec, ang[u]);
                 if (far)
                     acc[u] += v;
             }

@@ -15,7 +15,7 @@
 #define TVD_NODE 0.577350269189625731058868041146   // _tesseroid.pyx:27-28
 
 // Far-field record sizes (doubles per radial piece); see DESIGN.md "data layout".
-#define TVD_TEST_REC 8
+#define TVD_TEST_REC 4
 #define TVD_GLQ_REC 16
 #define TVD_TILE 64                         // pieces per shared-memory tile
 // far-field sweep launch shape: threads per block, points per thread, resident blocks per SM

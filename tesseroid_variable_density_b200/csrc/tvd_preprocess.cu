@@ -245,11 +245,11 @@ cudaError_t tvd_launch_scan(const int32_t *d_counts, int64_t *d_offsets, int64_t
 // ---------------------------------------------------------------------------------------------
 // K4: root records
 // ---------------------------------------------------------------------------------------------
-// test record  [8]: cos(lont) sin(lont) sinlatt coslatt rt^2 2*rt thr2 (pad)
+// test record  [4]: cx cy cz (Cartesian centre of the piece)  rt^2 - thr2
 //   thr2 is the conservative far-field threshold on the squared centre distance, see
 //   tvd_far.cu; pairs that do not clear it are re-examined with the literal test.
 // glq record  [16]: lonc0 lonc1 sinlatc0 sinlatc1 coslatc0 coslatc1 rc0 rc1 rc0^2 rc1^2
-//                   w00 w01 w10 w11 (w[j][k]) (pad) (pad)
+//                   w00 w01 w10 w11 (w[j][k])  same-extent flag (int64)  (pad)
 __global__ void __launch_bounds__(128)
 k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bounds,
               const int32_t *__restrict__ tess_kind, const double *__restrict__ tess_params,
@@ -280,20 +280,17 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
     const double Llat = rtop * acos(sin(TVD_D2R * n) * sin(TVD_D2R * s) +
                                     cos(TVD_D2R * n) * cos(TVD_D2R * s));
     // Conservative far-field threshold.  The literal test (divisions, :135,140) splits iff
-    // d <= ratio*Llon or d <= ratio*Llat (NaN sizes never split).  The sweep evaluates d^2
-    // with an absolute error far below 1 m^2, so d2 > thr^2*(1+1e-9) + 2 guarantees that the
-    // literal test says "no split"; everything else is deferred to the literal walk.
+    // d <= ratio*Llon or d <= ratio*Llat (NaN sizes never split).  The sweep evaluates
+    // d^2 = r^2 + rt^2 - 2 p.c from Cartesian position vectors with an absolute error far below
+    // 1 m^2, so d2 > thr^2*(1+1e-9) + 2 guarantees that the literal test says "no split";
+    // everything else is deferred to the literal walk.
     const double thr = fmax(ratio * Llon, ratio * Llat);    // fmax ignores a single NaN
     const double thr2 = thr * thr * (1.0 + 1e-9) + 2.0;     // NaN if both sizes are NaN
     double *tr = test_rec + TVD_TEST_REC * q;
-    tr[0] = cos(lont);
-    tr[1] = sin(lont);
-    tr[2] = sinlatt;
-    tr[3] = coslatt;
-    tr[4] = rt * rt;
-    tr[5] = 2.0 * rt;
-    tr[6] = thr2;
-    tr[7] = 0.0;
+    tr[0] = rt * (coslatt * cos(lont));     // centre of the piece, geocentric Cartesian
+    tr[1] = rt * (coslatt * sin(lont));
+    tr[2] = rt * sinlatt;
+    tr[3] = rt * rt - thr2;                 // a NaN threshold defers every pair of the piece
 
     // scale_nodes (_tesseroid.pyx:162-175)
     const double dlon = e - w, dlat = n - s, dr = top - bottom;
@@ -338,7 +335,10 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
             g[10 + 2 * j + k] = wjk;
         }
     }
-    g[14] = 0.0;
+    // flag (as a 64-bit integer): same lon/lat extent as the previous piece of the same tile,
+    // i.e. a further radial piece of the same tesseroid -> the sweep keeps its angular half
+    const bool same = (q % TVD_TILE) != 0 && parent[q - 1] == parent[q];
+    reinterpret_cast<long long *>(g)[14] = same ? 1 : 0;
     g[15] = 0.0;
 }
 
