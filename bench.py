@@ -39,8 +39,14 @@ METRIC = "tesseroid-point evals/sec (gz, exp density)"
 UNIT = "evals/s"
 NLAT = NLON = 1000
 SEED = 20190277
-# canonical algorithmic FP64 flop counts (convention v1, FMA = 2)
-F_TEST, F_GEOM, F_SETUP, F_GLQ_GZ = 76, 328, 223, 308
+# Algorithmic FP64 flops of one far-field gz (piece, point) pair, FMA = 2.
+#  * SURVEY.md section 8d (convention v1) ESTIMATED 384 = F_test 76 + F_glq 308 from guessed
+#    special-function weights and asked for them to be calibrated once with ncu on the first
+#    kernel and frozen.  The first kernel of round 1 (profiles/far_sweep_r1a_*.txt) executed
+#    29 DADD + 75 DMUL + 57 DFMA = 218 flops per pair: that calibrated figure is the frozen
+#    per-unit count (DESIGN.md "Measurement").
+F_PAIR_CALIBRATED = 218
+F_PAIR_V1_ESTIMATE = 384
 
 
 # ---------------------------------------------------------------------------------------------
@@ -352,8 +358,9 @@ def run_gpu(args):
         # canonical convention divided by its CUDA-event duration on its launch stream
         far_pairs = float(agg[_lib.STAT_NAMES.index("nodes")] - agg[_lib.STAT_NAMES.index("nonroot_nodes")]
                           - agg[_lib.STAT_NAMES.index("near_pairs")])
-        flops = far_pairs * (F_TEST + F_GLQ_GZ)
+        flops = far_pairs * F_PAIR_CALIBRATED
         achieved = flops / (far_ms * 1e-3) / 1e12 if far_ms > 0 else None
+        achieved_v1 = far_pairs * F_PAIR_V1_ESTIMATE / (far_ms * 1e-3) / 1e12 if far_ms > 0 else None
         peak = float(lib.tvd_measure_fp64_peak(local, 8192))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
@@ -371,7 +378,9 @@ def run_gpu(args):
                          "kernel": "far_sweep<gz>",
                          "kernel_ms_per_launch": far_ms / max(1, nfar.value),
                          "kernel_share_of_step": far_ms / ms,
-                         "flops_per_piece_pair": F_TEST + F_GLQ_GZ,
+                         "flops_per_piece_pair": F_PAIR_CALIBRATED,
+                         "piece_pairs_per_launch": far_pairs / max(1, nfar.value),
+                         "achieved_with_uncalibrated_v1_estimate_384": achieved_v1,
                          "peak_source": "DFMA microbenchmark run by this process "
                                         "(MEASURED_PEAKS.json has no FP64 figure)"},
             "e2e": {"value": float(n_tess) * P * args.steps * world / t_e2e, "unit": UNIT,

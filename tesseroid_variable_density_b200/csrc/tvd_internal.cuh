@@ -20,13 +20,13 @@
 #define TVD_TILE 64                         // pieces per shared-memory tile
 // far-field sweep launch shape: threads per block, points per thread, resident blocks per SM
 #ifndef TVD_FAR_THREADS
-#define TVD_FAR_THREADS 256
+#define TVD_FAR_THREADS 512
 #endif
 #ifndef TVD_FAR_PPT
 #define TVD_FAR_PPT 1
 #endif
 #ifndef TVD_FAR_MINBLOCKS
-#define TVD_FAR_MINBLOCKS 2
+#define TVD_FAR_MINBLOCKS 1
 #endif
 #define TVD_MAX_K1_PIECES 256               // cap on radial pieces of ONE tesseroid
 #define TVD_MAX_DEPTH 64                    // levels of the near-field subdivision stack
