@@ -85,67 +85,6 @@ __device__ __forceinline__ double rsqrt_fast(double x)
 // i.e. it agrees with glibc's cos, which the reference calls).  When every lane of the warp
 // has |x| <= pi/4 (regional models) no reduction is done at all.
 // ---------------------------------------------------------------------------------------------
-#define TVD_PIO4 0.78539816339744830962
-__device__ __forceinline__ double kcos(double x, double y)
-{
-    const double z = x * x;
-    double r = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    r = fma(z, r, -2.75573143513906633035e-07);
-    r = fma(z, r, 2.48015872894767294178e-05);
-    r = fma(z, r, -1.38888888888741095749e-03);
-    r = fma(z, r, 4.16666666666666019037e-02);
-    r = r * z;
-    const double hz = 0.5 * z;
-    const double w = 1.0 - hz;
-    return w + (((1.0 - w) - hz) + fma(z, r, -(x * y)));
-}
-__device__ __forceinline__ double kcos0(double x)      // tail y == 0
-{
-    const double z = x * x;
-    double r = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    r = fma(z, r, -2.75573143513906633035e-07);
-    r = fma(z, r, 2.48015872894767294178e-05);
-    r = fma(z, r, -1.38888888888741095749e-03);
-    r = fma(z, r, 4.16666666666666019037e-02);
-    r = r * z;
-    const double hz = 0.5 * z;
-    const double w = 1.0 - hz;
-    return w + fma(z, r, (1.0 - w) - hz);
-}
-__device__ __forceinline__ double ksin(double x, double y)
-{
-    const double z = x * x;
-    const double v = z * x;
-    double r = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    r = fma(z, r, 2.75573137070700676789e-06);
-    r = fma(z, r, -1.98412698298579493134e-04);
-    r = fma(z, r, 8.33333333332248946124e-03);
-    // x - ((z*(0.5*y - v*r) - y) - v*S1)
-    return x - ((z * fma(-v, r, 0.5 * y) - y) - v * -1.66666666666666324348e-01);
-}
-__device__ __forceinline__ double ksin0(double x)
-{
-    const double z = x * x;
-    const double v = z * x;
-    double r = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    r = fma(z, r, 2.75573137070700676789e-06);
-    r = fma(z, r, -1.98412698298579493134e-04);
-    r = fma(z, r, 8.33333333332248946124e-03);
-    r = fma(z, r, -1.66666666666666324348e-01);
-    return fma(v, r, x);
-}
-// general argument: returns quadrant, reduced argument r and its tail y (x = k*pi/2 + r + y)
-__device__ __forceinline__ int reduce_pio2(double x, double &r, double &y)
-{
-    const double t = fma(x, 6.36619772367581382433e-01, 6755399441055744.0);
-    const int k = __double2loint(t);
-    const double kd = t - 6755399441055744.0;
-    const double r0 = fma(-kd, 1.57079632673412561417e+00, x);    // exact
-    const double w = kd * 6.07710050650619224932e-11;
-    r = r0 - w;
-    y = (r0 - r) - w;
-    return k;
-}
 // cos (and, if WANT_SIN, sin) of two arguments.  Warp-uniform fast path for |x| <= pi/4.
 template <bool WANT_SIN>
 __device__ __forceinline__ void trig2(double x0, double x1, double &c0, double &c1, double &s0,

@@ -32,6 +32,107 @@
 #define TVD_MAX_DEPTH 64                    // levels of the near-field subdivision stack
 
 // ---------------------------------------------------------------------------------------------
+// sin / cos.  fdlibm kernels + Cody-Waite reduction by pi/2 with a 33-bit head (k*head exact)
+// keeping the reduction tail.  Error < 1 ulp, and equal to glibc's sin/cos -- what the
+// reference calls -- in 97-99 % of cases; libdevice's versions are used only for huge arguments.
+// ---------------------------------------------------------------------------------------------
+#define TVD_PIO4 0.78539816339744830962
+__device__ __forceinline__ double kcos(double x, double y)
+{
+    const double z = x * x;
+    double r = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    r = fma(z, r, -2.75573143513906633035e-07);
+    r = fma(z, r, 2.48015872894767294178e-05);
+    r = fma(z, r, -1.38888888888741095749e-03);
+    r = fma(z, r, 4.16666666666666019037e-02);
+    r = r * z;
+    const double hz = 0.5 * z;
+    const double w = 1.0 - hz;
+    return w + (((1.0 - w) - hz) + fma(z, r, -(x * y)));
+}
+__device__ __forceinline__ double kcos0(double x)      // tail y == 0
+{
+    const double z = x * x;
+    double r = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    r = fma(z, r, -2.75573143513906633035e-07);
+    r = fma(z, r, 2.48015872894767294178e-05);
+    r = fma(z, r, -1.38888888888741095749e-03);
+    r = fma(z, r, 4.16666666666666019037e-02);
+    r = r * z;
+    const double hz = 0.5 * z;
+    const double w = 1.0 - hz;
+    return w + fma(z, r, (1.0 - w) - hz);
+}
+__device__ __forceinline__ double ksin(double x, double y)
+{
+    const double z = x * x;
+    const double v = z * x;
+    double r = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    r = fma(z, r, 2.75573137070700676789e-06);
+    r = fma(z, r, -1.98412698298579493134e-04);
+    r = fma(z, r, 8.33333333332248946124e-03);
+    // x - ((z*(0.5*y - v*r) - y) - v*S1)
+    return x - ((z * fma(-v, r, 0.5 * y) - y) - v * -1.66666666666666324348e-01);
+}
+__device__ __forceinline__ double ksin0(double x)
+{
+    const double z = x * x;
+    const double v = z * x;
+    double r = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    r = fma(z, r, 2.75573137070700676789e-06);
+    r = fma(z, r, -1.98412698298579493134e-04);
+    r = fma(z, r, 8.33333333332248946124e-03);
+    r = fma(z, r, -1.66666666666666324348e-01);
+    return fma(v, r, x);
+}
+// general argument: returns quadrant, reduced argument r and its tail y (x = k*pi/2 + r + y)
+__device__ __forceinline__ int reduce_pio2(double x, double &r, double &y)
+{
+    const double t = fma(x, 6.36619772367581382433e-01, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    const double r0 = fma(-kd, 1.57079632673412561417e+00, x);    // exact
+    const double w = kd * 6.07710050650619224932e-11;
+    r = r0 - w;
+    y = (r0 - r) - w;
+    return k;
+}
+// scalar sin and cos of one argument (per-thread, no warp votes): K4, Phase B, densities
+__device__ __forceinline__ void tvd_sincos(double x, double &s, double &c)
+{
+    if (!(fabs(x) < 1.0e5)) {       // huge, inf or NaN
+        sincos(x, &s, &c);
+        return;
+    }
+    if (fabs(x) <= TVD_PIO4) {
+        s = ksin0(x);
+        c = kcos0(x);
+        return;
+    }
+    double r, y;
+    const int k = reduce_pio2(x, r, y);
+    const double cr = kcos(r, y), sr = ksin(r, y);
+    c = (k & 1) ? sr : cr;
+    if ((k + 1) & 2)
+        c = -c;
+    s = (k & 1) ? cr : sr;
+    if (k & 2)
+        s = -s;
+}
+__device__ __forceinline__ double tvd_sin(double x)
+{
+    double s, c;
+    tvd_sincos(x, s, c);
+    return s;
+}
+__device__ __forceinline__ double tvd_cos(double x)
+{
+    double s, c;
+    tvd_sincos(x, s, c);
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
 // density-in-depth models (tvd_density_kind), evaluated in the reference scripts' own
 // operation order (no contraction: the TU is built with -fmad=false)
 // ---------------------------------------------------------------------------------------------
@@ -47,7 +148,7 @@ __device__ __forceinline__ double tvd_density(int kind, const double *__restrict
     case TVD_DENS_EXP:
         return p[0] * exp(p[1] * (h - p[2]) / p[3]) + p[4];
     default:
-        return p[0] * sin(p[1] * h) + p[2];
+        return p[0] * tvd_sin(p[1] * h) + p[2];
     }
 }
 

@@ -274,11 +274,11 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
     const double rt = 0.5 * (top + bottom) + TVD_R;
     const double lont = TVD_D2R * 0.5 * (w + e);
     const double latt = TVD_D2R * 0.5 * (s + n);
-    const double sinlatt = sin(latt), coslatt = cos(latt);
+    const double sinlatt = tvd_sin(latt), coslatt = tvd_cos(latt);
     const double rtop = top + TVD_R;
-    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * cos(TVD_D2R * (e - w)));
-    const double Llat = rtop * acos(sin(TVD_D2R * n) * sin(TVD_D2R * s) +
-                                    cos(TVD_D2R * n) * cos(TVD_D2R * s));
+    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * tvd_cos(TVD_D2R * (e - w)));
+    const double Llat = rtop * acos(tvd_sin(TVD_D2R * n) * tvd_sin(TVD_D2R * s) +
+                                    tvd_cos(TVD_D2R * n) * tvd_cos(TVD_D2R * s));
     // Conservative far-field threshold.  The literal test (divisions, :135,140) splits iff
     // d <= ratio*Llon or d <= ratio*Llat (NaN sizes never split).  The sweep evaluates
     // d^2 = r^2 + rt^2 - 2 p.c from Cartesian position vectors with an absolute error far below
@@ -287,8 +287,8 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
     const double thr = fmax(ratio * Llon, ratio * Llat);    // fmax ignores a single NaN
     const double thr2 = thr * thr * (1.0 + 1e-9) + 2.0;     // NaN if both sizes are NaN
     double *tr = test_rec + TVD_TEST_REC * q;
-    tr[0] = rt * (coslatt * cos(lont));     // centre of the piece, geocentric Cartesian
-    tr[1] = rt * (coslatt * sin(lont));
+    tr[0] = rt * (coslatt * tvd_cos(lont));     // centre of the piece, geocentric Cartesian
+    tr[1] = rt * (coslatt * tvd_sin(lont));
     tr[2] = rt * sinlatt;
     tr[3] = rt * rt - thr2;                 // a NaN threshold defers every pair of the piece
 
@@ -302,8 +302,8 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
         lonc[i] = TVD_D2R * (0.5 * dlon * node + mlon);
         const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
-        sinlatc[i] = sin(latc);
-        coslatc[i] = cos(latc);
+        sinlatc[i] = tvd_sin(latc);
+        coslatc[i] = tvd_cos(latc);
         rc[i] = (0.5 * dr * node + mr);
         rcsq[i] = rc[i] * rc[i];
         dens[i] = tvd_density(kind, p, rc[i] - TVD_R);      // :274 (or the constant, :250)
