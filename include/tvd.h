@@ -177,6 +177,10 @@ double tvd_measure_fp64_peak(int device, int iters);
  * _tesseroid.pyx:242,401). */
 int tvd_debug_trig(int device, int64_t n, const double *x, double *cos_out, double *sin_out);
 
+/* Debug/test hook: the double-double sin (func 0), cos (1) and exp (2) that K1 uses for the
+ * density samples (tesseroid.py:259,294), evaluated on `device` for n host values. */
+int tvd_debug_math(int device, int func, int64_t n, const double *x, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,7 @@ SIGNATURES = {
     "tvd_far_kernel_ms": (C.c_double, [C.c_int, _lp]),
     "tvd_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
     "tvd_debug_trig": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp]),
+    "tvd_debug_math": (C.c_int, [C.c_int, C.c_int, C.c_int64, _dp, _dp]),
 }
 
 

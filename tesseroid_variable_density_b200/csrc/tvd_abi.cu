@@ -292,6 +292,28 @@ extern "C" int tvd_debug_trig(int device, int64_t n, const double *x, double *co
     return TVD_OK;
 }
 
+extern "C" int tvd_debug_math(int device, int func, int64_t n, const double *x, double *out)
+{
+    g_last_error.clear();
+    if (n < 0 || func < 0 || func > 2 || (n > 0 && (!x || !out)))
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_debug_math: bad argument");
+    if (tvd_device_count() <= device || device < 0)
+        return set_error(TVD_ERR_NO_DEVICE, "tvd_debug_math: no such CUDA device");
+    if (n == 0)
+        return TVD_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)n * 2 * sizeof(double)));
+    cudaError_t e = cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = tvd_debug_math_launch(func, n, d, d + n, nullptr);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(out, d + n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CUDA_TRY(e);
+    return TVD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ABI: model
 // ---------------------------------------------------------------------------------------------

@@ -152,6 +152,25 @@ __device__ __forceinline__ double tvd_density(int kind, const double *__restrict
     }
 }
 
+// The same models with sin/exp evaluated in double-double and rounded once (tvd_ddmath.cuh):
+// used where the last bit decides discrete outcomes (K1) and where it is free (K4).
+#include "tvd_ddmath.cuh"
+__device__ __forceinline__ double tvd_density_cr(int kind, const double *__restrict__ p, double h)
+{
+    switch (kind) {
+    case TVD_DENS_CONST:
+        return p[0];
+    case TVD_DENS_LINEAR: {
+        double r = h + p[1];
+        return p[0] * r + p[2];
+    }
+    case TVD_DENS_EXP:
+        return p[0] * dd_exp(p[1] * (h - p[2]) / p[3]) + p[4];
+    default:
+        return p[0] * dd_sin(p[1] * h) + p[2];
+    }
+}
+
 // canonical piece table (device, SoA), output of the K1 preprocessing
 struct PieceTable {
     int64_t n_tess = 0, n_pieces = 0;
@@ -216,6 +235,8 @@ cudaError_t tvd_launch_init_counts(const PieceTable &t, int64_t n_points, int32_
                                    cudaStream_t stream);
 double tvd_fp64_probe(int iters, cudaStream_t stream);
 cudaError_t tvd_debug_trig_launch(int64_t n, const double *d_x, double *d_c, double *d_s,
+                                  cudaStream_t stream);
+cudaError_t tvd_debug_math_launch(int func, int64_t n, const double *d_x, double *d_out,
                                   cudaStream_t stream);
 
 void tvd_count_launch(int n = 1);

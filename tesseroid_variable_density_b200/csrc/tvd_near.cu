@@ -15,6 +15,11 @@
 // how the points were sharded over blocks, groups or GPUs.
 #include "tvd_internal.cuh"
 
+// Near-field pairs are the worst-conditioned ones (cos psi and l^2 cancel hardest for the closest
+// cells), and there are few of them: all trigonometry of the literal walk is evaluated in
+// double-double and rounded once (tvd_ddmath.cuh), i.e. it equals glibc's result wherever glibc
+// rounds correctly.
+
 struct Level {
     double w, s, dlon, dlat;
     int nlon, nlat, next;
@@ -35,8 +40,8 @@ __device__ __forceinline__ void scale_nodes(double w, double e, double s, double
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
         o.lonc[i] = TVD_D2R * (0.5 * dlon * node + mlon);
         const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
-        o.sinlatc[i] = tvd_sin(latc);
-        o.coslatc[i] = tvd_cos(latc);
+        o.sinlatc[i] = dd_sin(latc);
+        o.coslatc[i] = dd_cos(latc);
         o.rc[i] = (0.5 * dr * node + mr);
     }
     o.scale = TVD_D2R * dlon * TVD_D2R * dlat * dr * 0.125;
@@ -56,10 +61,10 @@ __device__ double glq_literal(bool variable, int kind, const double *p, double l
     double result = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const double coslon = tvd_cos(lon - nd.lonc[i]);
+        const double coslon = dd_cos(lon - nd.lonc[i]);
         double sinlon = 0.0;
         if (FIELD == TVD_GY || FIELD == TVD_GXY || FIELD == TVD_GYY || FIELD == TVD_GYZ)
-            sinlon = tvd_sin(nd.lonc[i] - lon);
+            sinlon = dd_sin(nd.lonc[i] - lon);
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             const double kphi = coslat * nd.sinlatc[j] - sinlat * nd.coslatc[j] * coslon;
@@ -142,12 +147,12 @@ near_walk(const NearArgs a)
         // distance_n_size (:104-123)
         const double lont = TVD_D2R * 0.5 * (w + e);
         const double latt = TVD_D2R * 0.5 * (s + n);
-        const double sinlatt = tvd_sin(latt), coslatt = tvd_cos(latt);
-        const double cospsi = sinlat * sinlatt + coslat * coslatt * tvd_cos(lon - lont);
+        const double sinlatt = dd_sin(latt), coslatt = dd_cos(latt);
+        const double cospsi = sinlat * sinlatt + coslat * coslatt * dd_cos(lon - lont);
         const double distance = sqrt(radius * radius + rt * rt - 2 * radius * rt * cospsi);
-        const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * tvd_cos(TVD_D2R * (e - w)));
-        const double Llat = rtop * acos(tvd_sin(TVD_D2R * n) * tvd_sin(TVD_D2R * s) +
-                                        tvd_cos(TVD_D2R * n) * tvd_cos(TVD_D2R * s));
+        const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * dd_cos(TVD_D2R * (e - w)));
+        const double Llat = rtop * acos(dd_sin(TVD_D2R * n) * dd_sin(TVD_D2R * s) +
+                                        dd_cos(TVD_D2R * n) * dd_cos(TVD_D2R * s));
         // divisions (:129-146)
         int nlon = 1, nlat = 1;
         if (distance <= a.ratio * Llon) {

@@ -39,14 +39,14 @@ __device__ void divider_calculation(double top, double bottom, int kind, const d
     const double delta = top - bottom;
     const double step = delta / 100.0;
     const double range = rho_max - rho_min;
-    const double nd0 = (tvd_density(kind, p, bottom) - rho_min) / range;   // heights[0] == start
-    const double nd100 = (tvd_density(kind, p, top) - rho_min) / range;
+    const double nd0 = (tvd_density_cr(kind, p, bottom) - rho_min) / range;   // heights[0] == start
+    const double nd100 = (tvd_density_cr(kind, p, top) - rho_min) / range;
     const double slope = (nd100 - nd0) / (top - bottom);
     double best = -1.0, best_h = bottom;
     bool has_nan = false;
     for (int i = 0; i < 101; i++) {
         const double h = linspace101(bottom, top, delta, step, i);
-        const double nd = (tvd_density(kind, p, h) - rho_min) / range;
+        const double nd = (tvd_density_cr(kind, p, h) - rho_min) / range;
         const double line = slope * (h - bottom) + nd0;
         const double diff = fabs(nd - line);
         if (diff != diff) {                 // numpy max/argmax propagate the first NaN
@@ -93,9 +93,9 @@ k1_discretize(int64_t n_tess, const double *__restrict__ bounds, const int32_t *
         // tesseroid.py:258-264
         const double d = top - bottom, step = d / 100.0;
         bool has_nan = false;
-        rho_min = rho_max = tvd_density(kind, p, bottom);
+        rho_min = rho_max = tvd_density_cr(kind, p, bottom);
         for (int i = 0; i < 101; i++) {
-            const double rho = tvd_density(kind, p, linspace101(bottom, top, d, step, i));
+            const double rho = tvd_density_cr(kind, p, linspace101(bottom, top, d, step, i));
             if (rho != rho)
                 has_nan = true;
             if (rho < rho_min)
@@ -274,11 +274,11 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
     const double rt = 0.5 * (top + bottom) + TVD_R;
     const double lont = TVD_D2R * 0.5 * (w + e);
     const double latt = TVD_D2R * 0.5 * (s + n);
-    const double sinlatt = tvd_sin(latt), coslatt = tvd_cos(latt);
+    const double sinlatt = dd_sin(latt), coslatt = dd_cos(latt);
     const double rtop = top + TVD_R;
-    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * tvd_cos(TVD_D2R * (e - w)));
-    const double Llat = rtop * acos(tvd_sin(TVD_D2R * n) * tvd_sin(TVD_D2R * s) +
-                                    tvd_cos(TVD_D2R * n) * tvd_cos(TVD_D2R * s));
+    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * dd_cos(TVD_D2R * (e - w)));
+    const double Llat = rtop * acos(dd_sin(TVD_D2R * n) * dd_sin(TVD_D2R * s) +
+                                    dd_cos(TVD_D2R * n) * dd_cos(TVD_D2R * s));
     // Conservative far-field threshold.  The literal test (divisions, :135,140) splits iff
     // d <= ratio*Llon or d <= ratio*Llat (NaN sizes never split).  The sweep evaluates
     // d^2 = r^2 + rt^2 - 2 p.c from Cartesian position vectors with an absolute error far below
@@ -287,8 +287,8 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
     const double thr = fmax(ratio * Llon, ratio * Llat);    // fmax ignores a single NaN
     const double thr2 = thr * thr * (1.0 + 1e-9) + 2.0;     // NaN if both sizes are NaN
     double *tr = test_rec + TVD_TEST_REC * q;
-    tr[0] = rt * (coslatt * tvd_cos(lont));     // centre of the piece, geocentric Cartesian
-    tr[1] = rt * (coslatt * tvd_sin(lont));
+    tr[0] = rt * (coslatt * dd_cos(lont));     // centre of the piece, geocentric Cartesian
+    tr[1] = rt * (coslatt * dd_sin(lont));
     tr[2] = rt * sinlatt;
     tr[3] = rt * rt - thr2;                 // a NaN threshold defers every pair of the piece
 
@@ -302,11 +302,11 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
         lonc[i] = TVD_D2R * (0.5 * dlon * node + mlon);
         const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
-        sinlatc[i] = tvd_sin(latc);
-        coslatc[i] = tvd_cos(latc);
+        sinlatc[i] = dd_sin(latc);
+        coslatc[i] = dd_cos(latc);
         rc[i] = (0.5 * dr * node + mr);
         rcsq[i] = rc[i] * rc[i];
-        dens[i] = tvd_density(kind, p, rc[i] - TVD_R);      // :274 (or the constant, :250)
+        dens[i] = tvd_density_cr(kind, p, rc[i] - TVD_R);   // :274 (or the constant, :250)
     }
     const double scale = TVD_D2R * dlon * TVD_D2R * dlat * dr * 0.125;
     double *g = glq_rec + TVD_GLQ_REC * q;
@@ -372,6 +372,29 @@ cudaError_t tvd_launch_init_counts(const PieceTable &t, int64_t n_points, int32_
         return cudaSuccess;
     init_counts<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(t.n_tess, n_points,
                                                                  t.tess_npieces, counts);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug: the double-double sin / cos / exp, exposed so that tests can check them against an
+// arbitrary-precision reference
+// ---------------------------------------------------------------------------------------------
+__global__ void debug_math_kernel(int func, int64_t n, const double *__restrict__ x,
+                                  double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    out[i] = func == 0 ? dd_sin(x[i]) : func == 1 ? dd_cos(x[i]) : dd_exp(x[i]);
+}
+
+cudaError_t tvd_debug_math_launch(int func, int64_t n, const double *d_x, double *d_out,
+                                  cudaStream_t stream)
+{
+    if (n <= 0)
+        return cudaSuccess;
+    debug_math_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(func, n, d_x, d_out);
     tvd_count_launch();
     return cudaGetLastError();
 }

@@ -173,3 +173,61 @@ def test_own_trig_against_glibc():
         assert np.max(np.abs(c - cref) / np.spacing(np.abs(cref))) <= 1.0
         assert np.max(np.abs(s - sref) / np.spacing(np.abs(sref))) <= 1.0
         assert np.mean(c == cref) >= frac and np.mean(s == sref) >= frac
+
+
+def test_double_double_math_is_correctly_rounded():
+    """K1's sin/cos/exp (tvd_ddmath.cuh) against mpmath at 60 digits: correctly rounded for every
+    sample; hence equal to glibc wherever glibc itself rounds correctly (>= 99 %)."""
+    import math
+    import mpmath
+    mpmath.mp.dps = 60
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    sets = {
+        0: (np.concatenate([rng.uniform(-8, 8, 3000), rng.uniform(-2000, 2000, 2000),
+                            np.array([0.0, 1e-300, 1e-9, np.pi, 0.5 * np.pi, 710.0, 1e5])]),
+            mpmath.sin, math.sin),
+        1: (np.concatenate([rng.uniform(-8, 8, 3000), rng.uniform(-2000, 2000, 2000),
+                            np.array([0.0, 1e-9, np.pi, 0.5 * np.pi, 1e5])]), mpmath.cos, math.cos),
+        2: (np.concatenate([rng.uniform(-40, 5, 4000), rng.uniform(-690, 690, 1000),
+                            np.array([0.0, 1e-17, -1e-17, 1.0, -1.0])]), mpmath.exp, math.exp),
+    }
+    for func, (x, exact, libm) in sets.items():
+        x = np.ascontiguousarray(x)
+        out = np.empty_like(x)
+        assert lib.tvd_debug_math(0, func, x.size, _lib.ptr_f64(x), _lib.ptr_f64(out)) == 0
+        want = np.array([float(exact(mpmath.mpf(float(v)))) for v in x])   # float() rounds to nearest
+        assert np.array_equal(out, want), (func, int(np.sum(out != want)))
+        glibc = np.array([libm(float(v)) for v in x])
+        assert np.mean(out == glibc) >= 0.99
+
+
+def test_k1_tie_breaking_with_whole_periods(oracle_lib):
+    """A sine with a whole number of periods over the tesseroid has mathematically equal maxima
+    of |rho_n - line|; the split list is then decided by the last bit of sin()."""
+    from tesseroid_variable_density_b200.model import FlatModel
+    rng = np.random.default_rng(7)
+    n = 300
+    tops = rng.uniform(-1000, 0, n)
+    bots = tops - rng.uniform(5000, 50000, n)
+    bounds = np.zeros((n, 6))
+    bounds[:, 1] = 1
+    bounds[:, 3] = 1
+    bounds[:, 4], bounds[:, 5] = tops, bots
+    kinds = np.full(n, D.SINE, dtype=np.int32)
+    params = np.zeros((n, 5))
+    params[:, 0] = 1650.
+    params[:, 1] = 2 * np.pi * rng.integers(1, 5, n) / (tops - bots)
+    params[:, 2] = 1650.
+    for delta in (0.1, 1e-2):
+        pm = tesseroid.PreparedModel(FlatModel(bounds, kinds, params), delta=delta)
+        t, b, parent = pm.pieces()
+        pm.close()
+        pos, bad = 0, 0
+        for i in range(n):
+            ot, ob = oracle_lib.density_discretize(tops[i], bots[i], kinds[i], params[i], delta)
+            k = int(np.sum(parent == i))
+            if k != len(ot) or not (np.array_equal(t[pos:pos + k], ot) and np.array_equal(b[pos:pos + k], ob)):
+                bad += 1
+            pos += k
+        assert bad == 0, "%d of %d tesseroids split differently at delta=%g" % (bad, n, delta)

@@ -52,7 +52,7 @@ def run_both(oracle, mesh, grid, fields, delta, ratios=None, counts=True):
     for field, (g, o) in out.items():
         fam = FAMILY[field]
         s = max(scale[field], scale.get(fam, 0.0))
-        rel = np.max(np.abs(g[0] - o[0])) / s
+        rel = np.max(np.abs(g[0] - o[0])) / s if s > 0 else float(np.max(np.abs(g[0] - o[0])))
         ceq = np.array_equal(g[2], o[2]) if counts else True
         seq = all(g[1][k] == o[1][k] for k in COUNT_KEYS)
         res[field] = (g[0], o[0], rel, ceq, seq)
