@@ -143,6 +143,28 @@ int tvd_forward(int field, tvd_model *model, int64_t n_points, const double *lon
                 double *result, int64_t *stats, int32_t *leaf_counts);
 
 /*
+ * Several fields of the same model on the same points in ONE far-field sweep:
+ * the fields share the far test, the angular half of the quadrature, l^2 and its inverse square
+ * root; each field keeps its own distance-size ratio, near-field queue and literal walk, and its
+ * values are bit-identical to a separate tvd_forward call.  The reference needs one full pass
+ * per field (tesseroid.py:377,435,493,556).
+ *
+ *   n_fields, fields, ratios   distinct tvd_field ids and the ratio D of each
+ *   results      [n_fields][P] in the caller's field order, kernel units, OVERWRITTEN
+ *   stats        NULL or int64[n_fields][TVD_NSTATS]
+ * Compiled-in sets: any single field; {potential, gz, gzz}; {potential, gx, gy, gz};
+ * {gx, gy, gz}; the six tensor components.  Other sets return TVD_ERR_BAD_ARGUMENT
+ * (tvd_fused_supported tells in advance).
+ */
+int tvd_forward_fused(int n_fields, const int *fields, const double *ratios, tvd_model *model,
+                      int64_t n_points, const double *lon_rad, const double *sinlat,
+                      const double *coslat, const double *radius, int stack_size, int n_devices,
+                      const int *device_ids, double *results, int64_t *stats);
+
+/* 1 if tvd_forward_fused accepts this set of fields, else 0. */
+int tvd_fused_supported(int n_fields, const int *fields);
+
+/*
  * Same computation with DEVICE-resident point arrays and result on `device`, enqueued on
  * `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).  Used by the
  * one-process-per-GPU launcher (each rank owns a contiguous point shard) and by bench.py for

@@ -39,6 +39,9 @@ SIGNATURES = {
     "tvd_model_get_pieces": (C.c_int, [C.c_void_p, _dp, _dp, _ip]),
     "tvd_forward": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_double,
                               C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _lp, _ip]),
+    "tvd_forward_fused": (C.c_int, [C.c_int, C.POINTER(C.c_int), _dp, C.c_void_p, C.c_int64, _dp,
+                                    _dp, _dp, _dp, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _lp]),
+    "tvd_fused_supported": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "tvd_forward_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                                      C.c_int, C.c_void_p, _lp, C.c_void_p]),

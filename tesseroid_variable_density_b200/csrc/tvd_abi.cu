@@ -73,9 +73,10 @@ struct DeviceCtx {
     int device = -1;
     bool has_table = false;
     PieceTable tab;
-    int packed_field = -1;
-    double packed_ratio = 0.0;
-    Buf test_rec, glq_rec;
+    bool glq_packed = false;
+    int packed_nf = 0;
+    double packed_ratio[TVD_MAX_FUSED] = {0};
+    Buf test_rec, glq_rec, geom;
     Buf far_out, queue, keys_sorted, pair_result, sort_temp, counters;
     Buf pts, result, counts;
     unsigned long long qcap_hint = 0;
@@ -114,6 +115,7 @@ static void free_ctx(DeviceCtx *c)
     free_table(c->tab);
     c->test_rec.release();
     c->glq_rec.release();
+    c->geom.release();
     c->far_out.release();
     c->queue.release();
     c->keys_sorted.release();
@@ -479,22 +481,32 @@ extern "C" int tvd_plan_groups(const tvd_model *m, int64_t n_points_total)
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward on one device (device pointers), the core
+// forward on one device (device pointers), the core: nf fields in one far-field sweep
 // ---------------------------------------------------------------------------------------------
-static int forward_core(tvd_model *m, DeviceCtx *c, int field, int64_t P, const double *d_lon,
-                        const double *d_sinlat, const double *d_coslat, const double *d_radius,
-                        double ratio, int stack_size, int n_groups, double *d_result,
-                        int64_t *stats, int32_t *d_leaf_counts, cudaStream_t stream)
+struct FieldSet {
+    int nf = 0;
+    int field[TVD_MAX_FUSED];       // ascending field ids (= the sweep's slot order)
+    double ratio[TVD_MAX_FUSED];
+    int mask = 0;
+};
+
+static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t P,
+                        const double *d_lon, const double *d_sinlat, const double *d_coslat,
+                        const double *d_radius, int stack_size, int n_groups,
+                        double *const *d_results /*[nf]*/, int64_t *stats /*[nf][TVD_NSTATS]*/,
+                        int32_t *d_leaf_counts, cudaStream_t stream)
 {
     const int64_t Q = m->n_pieces;
+    const int nf = fs.nf;
     if (stats)
-        memset(stats, 0, TVD_NSTATS * sizeof(int64_t));
+        memset(stats, 0, (size_t)nf * TVD_NSTATS * sizeof(int64_t));
     if (P == 0)
         return TVD_OK;
     if (P > 0x7fffffffLL)
         return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: more than 2^31-1 points per device");
     if (Q == 0) {
-        CUDA_TRY(cudaMemsetAsync(d_result, 0, P * sizeof(double), stream));
+        for (int f = 0; f < nf; f++)
+            CUDA_TRY(cudaMemsetAsync(d_results[f], 0, P * sizeof(double), stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         return TVD_OK;
     }
@@ -505,17 +517,31 @@ static int forward_core(tvd_model *m, DeviceCtx *c, int field, int64_t P, const 
     // groups that would start beyond Q are dropped (they would add exact zeros)
     n_groups = (int)((Q + ppg - 1) / ppg);
 
-    // K4: root records for (field, ratio), cached
-    if (c->packed_field != field || c->packed_ratio != ratio) {
-        CUDA_TRY(c->test_rec.reserve((size_t)Q * TVD_TEST_REC * sizeof(double)));
+    // K4: GLQ records once per model, test records per (field set, ratios)
+    if (!c->glq_packed) {
         CUDA_TRY(c->glq_rec.reserve((size_t)Q * TVD_GLQ_REC * sizeof(double)));
-        CUDA_TRY(tvd_launch_pack(field, c->tab, ratio, c->test_rec.as<double>(),
-                                 c->glq_rec.as<double>(), stream));
-        c->packed_field = field;
-        c->packed_ratio = ratio;
+        CUDA_TRY(c->geom.reserve((size_t)Q * 5 * sizeof(double)));
+        CUDA_TRY(tvd_launch_pack_glq(c->tab, c->glq_rec.as<double>(), c->geom.as<double>(), stream));
+        c->glq_packed = true;
     }
-    CUDA_TRY(c->far_out.reserve((size_t)n_groups * P * sizeof(double)));
-    CUDA_TRY(c->counters.reserve(16 * sizeof(unsigned long long)));
+    bool same_test = c->packed_nf == nf;
+    for (int f = 0; f < nf && same_test; f++)
+        same_test = c->packed_ratio[f] == fs.ratio[f];
+    if (!same_test) {
+        RatioList rl;
+        rl.nf = nf;
+        for (int f = 0; f < TVD_MAX_FUSED; f++)
+            rl.ratio[f] = f < nf ? fs.ratio[f] : 0.0;
+        CUDA_TRY(c->test_rec.reserve((size_t)Q * tvd_test_rec_len(nf) * sizeof(double)));
+        CUDA_TRY(tvd_launch_pack_test(c->tab, c->geom.as<double>(), rl, c->test_rec.as<double>(),
+                                      stream));
+        c->packed_nf = nf;
+        for (int f = 0; f < nf; f++)
+            c->packed_ratio[f] = fs.ratio[f];
+    }
+    CUDA_TRY(c->far_out.reserve((size_t)nf * n_groups * P * sizeof(double)));
+    const int n_cnt = 8 + 8 * TVD_MAX_FUSED;
+    CUDA_TRY(c->counters.reserve(n_cnt * sizeof(unsigned long long)));
     unsigned long long qcap = c->qcap_hint;
     if (qcap == 0) {
         qcap = 16ull * (unsigned long long)P;
@@ -526,13 +552,14 @@ static int forward_core(tvd_model *m, DeviceCtx *c, int field, int64_t P, const 
     if (qcap > all_pairs)
         qcap = all_pairs;
 
-    unsigned long long *d_cnt = c->counters.as<unsigned long long>();   // [0]=queue count, [8..]=near
-    unsigned long long nq = 0;
+    // [0..nf) = queue counts, [8 + 8 f ..) = near-field counters of field slot f
+    unsigned long long *d_cnt = c->counters.as<unsigned long long>();
+    unsigned long long nq[TVD_MAX_FUSED] = {0};
     for (int attempt = 0; attempt < 2; attempt++) {
-        CUDA_TRY(c->queue.reserve((size_t)qcap * sizeof(unsigned long long)));
-        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(unsigned long long), stream));
+        CUDA_TRY(c->queue.reserve((size_t)nf * qcap * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, n_cnt * sizeof(unsigned long long), stream));
         FarArgs fa;
-        fa.field = field;
+        fa.mask = fs.mask;
         fa.n_points = P;
         fa.lon = d_lon;
         fa.sinlat = d_sinlat;
@@ -550,7 +577,8 @@ static int forward_core(tvd_model *m, DeviceCtx *c, int field, int64_t P, const 
         CUDA_TRY(cudaEventRecord(c->ev0, stream));
         CUDA_TRY(tvd_launch_far(fa, stream));
         CUDA_TRY(cudaEventRecord(c->ev1, stream));
-        CUDA_TRY(cudaMemcpyAsync(&nq, d_cnt, sizeof(nq), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(nq, d_cnt, nf * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) {
@@ -558,69 +586,129 @@ static int forward_core(tvd_model *m, DeviceCtx *c, int field, int64_t P, const 
             g_far_ms += ms;
             g_far_launches += 1;
         }
-        if (nq <= qcap)
+        unsigned long long worst = 0;
+        for (int f = 0; f < nf; f++)
+            worst = nq[f] > worst ? nq[f] : worst;
+        if (worst <= qcap)
             break;
         // queue overflow: the exact size is now known, run the sweep once more
-        qcap = nq;
-        c->qcap_hint = nq + nq / 4;
+        qcap = worst;
+        c->qcap_hint = worst + worst / 4;
         if (attempt == 1)
             return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: near-field queue overflow twice");
     }
 
-    const unsigned long long *d_keys = nullptr;
-    if (nq > 0) {
-        CUDA_TRY(c->keys_sorted.reserve((size_t)nq * sizeof(unsigned long long)));
-        CUDA_TRY(c->pair_result.reserve((size_t)nq * sizeof(double)));
-        int pbits = 1;
-        while (pbits < 32 && (1ll << pbits) < P)
-            pbits++;
-        size_t temp_bytes = 0;
-        CUDA_TRY(tvd_sort_keys(nullptr, temp_bytes, c->queue.as<unsigned long long>(),
-                               c->keys_sorted.as<unsigned long long>(), (int64_t)nq, 32 + pbits,
-                               stream));
-        CUDA_TRY(c->sort_temp.reserve(temp_bytes ? temp_bytes : 16));
-        CUDA_TRY(tvd_sort_keys(c->sort_temp.p, temp_bytes, c->queue.as<unsigned long long>(),
-                               c->keys_sorted.as<unsigned long long>(), (int64_t)nq, 32 + pbits,
-                               stream));
-        d_keys = c->keys_sorted.as<unsigned long long>();
-        NearArgs na;
-        na.field = field;
-        na.n_pairs = (int64_t)nq;
-        na.keys = d_keys;
-        na.lon = d_lon;
-        na.sinlat = d_sinlat;
-        na.coslat = d_coslat;
-        na.radius = d_radius;
-        na.table = c->tab;
-        na.ratio = ratio;
-        na.stack_size = stack_size;
-        na.pair_result = c->pair_result.as<double>();
-        na.counters = d_cnt + 8;
-        na.leaf_counts = d_leaf_counts;
-        na.n_points = P;
-        CUDA_TRY(tvd_launch_near(na, stream));
+    int pbits = 1;
+    while (pbits < 32 && (1ll << pbits) < P)
+        pbits++;
+    for (int f = 0; f < nf; f++) {
+        const unsigned long long *d_keys = nullptr;
+        const unsigned long long n = nq[f];
+        if (n > 0) {
+            const unsigned long long *q_in = c->queue.as<unsigned long long>() + (size_t)f * qcap;
+            CUDA_TRY(c->keys_sorted.reserve((size_t)n * sizeof(unsigned long long)));
+            CUDA_TRY(c->pair_result.reserve((size_t)n * sizeof(double)));
+            size_t temp_bytes = 0;
+            CUDA_TRY(tvd_sort_keys(nullptr, temp_bytes, q_in,
+                                   c->keys_sorted.as<unsigned long long>(), (int64_t)n, 32 + pbits,
+                                   stream));
+            CUDA_TRY(c->sort_temp.reserve(temp_bytes ? temp_bytes : 16));
+            CUDA_TRY(tvd_sort_keys(c->sort_temp.p, temp_bytes, q_in,
+                                   c->keys_sorted.as<unsigned long long>(), (int64_t)n, 32 + pbits,
+                                   stream));
+            d_keys = c->keys_sorted.as<unsigned long long>();
+            NearArgs na;
+            na.field = fs.field[f];
+            na.n_pairs = (int64_t)n;
+            na.keys = d_keys;
+            na.lon = d_lon;
+            na.sinlat = d_sinlat;
+            na.coslat = d_coslat;
+            na.radius = d_radius;
+            na.table = c->tab;
+            na.ratio = fs.ratio[f];
+            na.stack_size = stack_size;
+            na.pair_result = c->pair_result.as<double>();
+            na.counters = d_cnt + 8 + 8 * f;
+            na.leaf_counts = d_leaf_counts;
+            na.n_points = P;
+            CUDA_TRY(tvd_launch_near(na, stream));
+        }
+        CUDA_TRY(tvd_launch_combine(P, n_groups,
+                                    c->far_out.as<double>() + (size_t)f * n_groups * P,
+                                    (int64_t)n, d_keys, c->pair_result.as<double>(),
+                                    d_results[f], stream));
+        // keys_sorted / pair_result are reused by the next field: the stream orders the kernels
     }
-    CUDA_TRY(tvd_launch_combine(P, n_groups, c->far_out.as<double>(), (int64_t)nq, d_keys,
-                                c->pair_result.as<double>(), d_result, stream));
-    unsigned long long h_cnt[16];
+    unsigned long long h_cnt[8 + 8 * TVD_MAX_FUSED];
     CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    if (h_cnt[8 + 4] != 0)
-        return set_error(TVD_ERR_STACK_OVERFLOW, "Tesseroid stack overflow");
+    for (int f = 0; f < nf; f++)
+        if (h_cnt[8 + 8 * f + 4] != 0)
+            return set_error(TVD_ERR_STACK_OVERFLOW, "Tesseroid stack overflow");
     if (stats) {
-        const int64_t far_pairs = (int64_t)(all_pairs - nq);
-        const int64_t near_nodes = (int64_t)h_cnt[8 + 0], near_leaves = (int64_t)h_cnt[8 + 1];
-        stats[TVD_ST_NODES] = far_pairs + near_nodes;
-        stats[TVD_ST_LEAVES] = far_pairs + near_leaves;
-        stats[TVD_ST_SPLITS] = (int64_t)h_cnt[8 + 2];
-        stats[TVD_ST_TOO_SMALL] = (int64_t)h_cnt[8 + 3];
-        stats[TVD_ST_PIECES] = Q;
-        stats[TVD_ST_NONROOT_NODES] = near_nodes - (int64_t)nq;
-        // h_cnt[8+5] = walked pairs whose root was integrated after all (one root leaf each)
-        stats[TVD_ST_NONROOT_LEAVES] = near_leaves - (int64_t)h_cnt[8 + 5];
-        stats[TVD_ST_NEAR_PAIRS] = (int64_t)nq;
+        for (int f = 0; f < nf; f++) {
+            const unsigned long long *hc = h_cnt + 8 + 8 * f;
+            int64_t *st = stats + (size_t)f * TVD_NSTATS;
+            const int64_t far_pairs = (int64_t)(all_pairs - nq[f]);
+            const int64_t near_nodes = (int64_t)hc[0], near_leaves = (int64_t)hc[1];
+            st[TVD_ST_NODES] = far_pairs + near_nodes;
+            st[TVD_ST_LEAVES] = far_pairs + near_leaves;
+            st[TVD_ST_SPLITS] = (int64_t)hc[2];
+            st[TVD_ST_TOO_SMALL] = (int64_t)hc[3];
+            st[TVD_ST_PIECES] = Q;
+            st[TVD_ST_NONROOT_NODES] = near_nodes - (int64_t)nq[f];
+            // hc[5] = walked pairs whose root was integrated after all (one root leaf each)
+            st[TVD_ST_NONROOT_LEAVES] = near_leaves - (int64_t)hc[5];
+            st[TVD_ST_NEAR_PAIRS] = (int64_t)nq[f];
+        }
     }
     return TVD_OK;
+}
+
+// validate and order a list of fields; a set the sweep is not compiled for is rejected
+static int make_field_set(int n_fields, const int *fields, const double *ratios, FieldSet &fs,
+                          int *order /*[n_fields]: slot of the caller's i-th field*/)
+{
+    if (n_fields < 1 || n_fields > TVD_MAX_FUSED || !fields || !ratios)
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: bad field list");
+    fs.nf = n_fields;
+    fs.mask = 0;
+    for (int i = 0; i < n_fields; i++) {
+        if (fields[i] < 0 || fields[i] >= TVD_NFIELDS || !(ratios[i] > 0) ||
+            (fs.mask & (1 << fields[i])))
+            return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: bad field or ratio");
+        fs.mask |= 1 << fields[i];
+    }
+    if (!tvd_far_mask_supported(fs.mask))
+        return set_error(TVD_ERR_BAD_ARGUMENT,
+                         "tvd_forward_fused: this combination of fields is not compiled in");
+    int slot = 0;
+    for (int f = 0; f < TVD_NFIELDS; f++) {
+        if (!(fs.mask & (1 << f)))
+            continue;
+        for (int i = 0; i < n_fields; i++)
+            if (fields[i] == f) {
+                fs.field[slot] = f;
+                fs.ratio[slot] = ratios[i];
+                order[i] = slot;
+            }
+        slot++;
+    }
+    return TVD_OK;
+}
+
+extern "C" int tvd_fused_supported(int n_fields, const int *fields)
+{
+    if (n_fields < 1 || n_fields > TVD_MAX_FUSED || !fields)
+        return 0;
+    int mask = 0;
+    for (int i = 0; i < n_fields; i++) {
+        if (fields[i] < 0 || fields[i] >= TVD_NFIELDS || (mask & (1 << fields[i])))
+            return 0;
+        mask |= 1 << fields[i];
+    }
+    return tvd_far_mask_supported(mask) ? 1 : 0;
 }
 
 extern "C" int tvd_forward_device(int field, tvd_model *m, int device, int64_t n_points,
@@ -632,21 +720,29 @@ extern "C" int tvd_forward_device(int field, tvd_model *m, int device, int64_t n
     g_last_error.clear();
     if (!m || field < 0 || field >= TVD_NFIELDS || n_points < 0 || !(ratio > 0))
         return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward_device: bad argument");
+    FieldSet fs;
+    int order[1];
+    int rc = make_field_set(1, &field, &ratio, fs, order);
+    if (rc)
+        return rc;
     DeviceCtx *c = nullptr;
-    int rc = get_ctx(m, device, &c);
+    rc = get_ctx(m, device, &c);
     if (rc)
         return rc;
     std::lock_guard<std::mutex> lock(c->mu);
     CUDA_TRY(cudaSetDevice(device));
-    return forward_core(m, c, field, n_points, d_lon, d_sinlat, d_coslat, d_radius, ratio,
-                        stack_size, n_groups, d_result, stats, nullptr, (cudaStream_t)stream);
+    double *res[1] = {d_result};
+    return forward_core(m, c, fs, n_points, d_lon, d_sinlat, d_coslat, d_radius, stack_size,
+                        n_groups, res, stats, nullptr, (cudaStream_t)stream);
 }
 
-// one device's share of tvd_forward: host slices in, host slice out
-static int forward_host_slice(tvd_model *m, int device, int field, int64_t P, int64_t p0,
-                              int64_t P_total, const double *lon, const double *sinlat,
-                              const double *coslat, const double *radius, double ratio,
-                              int stack_size, int n_groups, double *result, int64_t *stats,
+// one device's share of tvd_forward: host slices in, host slices out
+static int forward_host_slice(tvd_model *m, int device, const FieldSet &fs, const int *order,
+                              int n_fields, int64_t P, int64_t p0, int64_t P_total,
+                              const double *lon, const double *sinlat, const double *coslat,
+                              const double *radius, int stack_size, int n_groups,
+                              double *results /*[n_fields][P_total], caller order*/,
+                              int64_t *stats /*[n_fields][TVD_NSTATS], slot order*/,
                               int32_t *leaf_counts)
 {
     DeviceCtx *c = nullptr;
@@ -656,11 +752,11 @@ static int forward_host_slice(tvd_model *m, int device, int field, int64_t P, in
     std::lock_guard<std::mutex> lock(c->mu);
     CUDA_TRY(cudaSetDevice(device));
     if (stats)
-        memset(stats, 0, TVD_NSTATS * sizeof(int64_t));
+        memset(stats, 0, (size_t)n_fields * TVD_NSTATS * sizeof(int64_t));
     if (P == 0)
         return TVD_OK;
     CUDA_TRY(c->pts.reserve((size_t)P * 4 * sizeof(double)));
-    CUDA_TRY(c->result.reserve((size_t)P * sizeof(double)));
+    CUDA_TRY(c->result.reserve((size_t)n_fields * P * sizeof(double)));
     double *d_pts = c->pts.as<double>();
     const double *src[4] = {lon + p0, sinlat + p0, coslat + p0, radius + p0};
     for (int k = 0; k < 4; k++)
@@ -672,12 +768,16 @@ static int forward_host_slice(tvd_model *m, int device, int field, int64_t P, in
         d_counts = c->counts.as<int32_t>();
         CUDA_TRY(tvd_launch_init_counts(c->tab, P, d_counts, c->stream));
     }
-    rc = forward_core(m, c, field, P, d_pts, d_pts + P, d_pts + 2 * P, d_pts + 3 * P, ratio,
-                      stack_size, n_groups, c->result.as<double>(), stats, d_counts, c->stream);
+    double *d_res[TVD_MAX_FUSED];
+    for (int f = 0; f < n_fields; f++)
+        d_res[f] = c->result.as<double>() + (size_t)f * P;
+    rc = forward_core(m, c, fs, P, d_pts, d_pts + P, d_pts + 2 * P, d_pts + 3 * P, stack_size,
+                      n_groups, d_res, stats, d_counts, c->stream);
     if (rc)
         return rc;
-    CUDA_TRY(cudaMemcpyAsync(result + p0, c->result.p, P * sizeof(double), cudaMemcpyDeviceToHost,
-                             c->stream));
+    for (int i = 0; i < n_fields; i++)
+        CUDA_TRY(cudaMemcpyAsync(results + (size_t)i * P_total + p0, d_res[order[i]],
+                                 P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (leaf_counts && m->n_tess > 0)
         CUDA_TRY(cudaMemcpy2DAsync(leaf_counts + p0, (size_t)P_total * sizeof(int32_t), d_counts,
                                    (size_t)P * sizeof(int32_t), (size_t)P * sizeof(int32_t),
@@ -686,20 +786,28 @@ static int forward_host_slice(tvd_model *m, int device, int field, int64_t P, in
     return TVD_OK;
 }
 
-extern "C" int tvd_forward(int field, tvd_model *m, int64_t n_points, const double *lon,
-                           const double *sinlat, const double *coslat, const double *radius,
-                           double ratio, int stack_size, int n_devices, const int *device_ids,
-                           double *result, int64_t *stats, int32_t *leaf_counts)
+static int forward_host(int n_fields, const int *fields, const double *ratios, tvd_model *m,
+                        int64_t n_points, const double *lon, const double *sinlat,
+                        const double *coslat, const double *radius, int stack_size,
+                        int n_devices, const int *device_ids, double *results, int64_t *stats,
+                        int32_t *leaf_counts)
 {
     g_last_error.clear();
-    if (!m || field < 0 || field >= TVD_NFIELDS || n_points < 0 || !(ratio > 0) || n_devices < 1 ||
-        (n_points > 0 && (!lon || !sinlat || !coslat || !radius || !result)))
+    if (!m || n_points < 0 || n_devices < 1 ||
+        (n_points > 0 && (!lon || !sinlat || !coslat || !radius || !results)))
         return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: bad argument");
+    FieldSet fs;
+    int order[TVD_MAX_FUSED];
+    int rc = make_field_set(n_fields, fields, ratios, fs, order);
+    if (rc)
+        return rc;
+    if (leaf_counts && n_fields != 1)
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward: leaf counts need a single field");
     const int ndev_avail = tvd_device_count();
     if (ndev_avail == 0)
         return set_error(TVD_ERR_NO_DEVICE, "tvd_forward: no CUDA device (no CPU fallback)");
     if (stats)
-        memset(stats, 0, TVD_NSTATS * sizeof(int64_t));
+        memset(stats, 0, (size_t)n_fields * TVD_NSTATS * sizeof(int64_t));
     if (n_points == 0)
         return TVD_OK;
     int nparts = n_devices;
@@ -715,13 +823,14 @@ extern "C" int tvd_forward(int field, tvd_model *m, int64_t n_points, const doub
     const int64_t chunk = n_points / nparts;
     std::vector<int> rcs(nparts, 0);
     std::vector<std::string> errs(nparts);
-    std::vector<std::vector<int64_t>> st(nparts, std::vector<int64_t>(TVD_NSTATS, 0));
+    std::vector<std::vector<int64_t>> st(nparts,
+                                         std::vector<int64_t>((size_t)n_fields * TVD_NSTATS, 0));
     auto work = [&](int d) {
         const int id = device_ids ? device_ids[d] : d;
         const int64_t p0 = (int64_t)d * chunk;
         const int64_t p1 = (d == nparts - 1) ? n_points : p0 + chunk;
-        rcs[d] = forward_host_slice(m, id, field, p1 - p0, p0, n_points, lon, sinlat, coslat,
-                                    radius, ratio, stack_size, n_groups, result, st[d].data(),
+        rcs[d] = forward_host_slice(m, id, fs, order, n_fields, p1 - p0, p0, n_points, lon, sinlat,
+                                    coslat, radius, stack_size, n_groups, results, st[d].data(),
                                     leaf_counts);
         if (rcs[d])
             errs[d] = g_last_error;
@@ -741,10 +850,32 @@ extern "C" int tvd_forward(int field, tvd_model *m, int64_t n_points, const doub
             return rcs[d];
         }
     if (stats) {
-        for (int d = 0; d < nparts; d++)
-            for (int k = 0; k < TVD_NSTATS; k++)
-                stats[k] += st[d][k];
-        stats[TVD_ST_PIECES] = m->n_pieces;
+        for (int i = 0; i < n_fields; i++) {
+            int64_t *out = stats + (size_t)i * TVD_NSTATS;
+            for (int d = 0; d < nparts; d++)
+                for (int k = 0; k < TVD_NSTATS; k++)
+                    out[k] += st[d][(size_t)order[i] * TVD_NSTATS + k];
+            out[TVD_ST_PIECES] = m->n_pieces;
+        }
     }
     return TVD_OK;
+}
+
+extern "C" int tvd_forward(int field, tvd_model *m, int64_t n_points, const double *lon,
+                           const double *sinlat, const double *coslat, const double *radius,
+                           double ratio, int stack_size, int n_devices, const int *device_ids,
+                           double *result, int64_t *stats, int32_t *leaf_counts)
+{
+    return forward_host(1, &field, &ratio, m, n_points, lon, sinlat, coslat, radius, stack_size,
+                        n_devices, device_ids, result, stats, leaf_counts);
+}
+
+extern "C" int tvd_forward_fused(int n_fields, const int *fields, const double *ratios,
+                                 tvd_model *m, int64_t n_points, const double *lon,
+                                 const double *sinlat, const double *coslat, const double *radius,
+                                 int stack_size, int n_devices, const int *device_ids,
+                                 double *results, int64_t *stats)
+{
+    return forward_host(n_fields, fields, ratios, m, n_points, lon, sinlat, coslat, radius,
+                        stack_size, n_devices, device_ids, results, stats, nullptr);
 }

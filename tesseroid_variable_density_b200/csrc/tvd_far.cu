@@ -133,12 +133,42 @@ __device__ __forceinline__ void trig2(double x0, double x1, double &c0, double &
     }
 }
 
-template <int FIELD>
-struct FieldTraits {
-    static constexpr bool needs_sinlon = (FIELD == TVD_GY || FIELD == TVD_GXY ||
-                                          FIELD == TVD_GYY || FIELD == TVD_GYZ);
-    static constexpr bool needs_kphi = (FIELD == TVD_GX || FIELD == TVD_GXX ||
-                                        FIELD == TVD_GXY || FIELD == TVD_GXZ);
+// ---------------------------------------------------------------------------------------------
+// The sweep is compiled for a MASK of fields (bit f = tvd_field f).  A single field is the
+// one-bit mask; fused sets (e.g. potential + gz + gzz) share the far test, the angular half, l^2
+// and its inverse square root between their fields.  Per field the arithmetic is the same in
+// every mask, so a field's far-field sum does not depend on which other fields ride along.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int mask_count(int m)
+{
+    int c = 0;
+    for (int f = 0; f < TVD_NFIELDS; f++)
+        c += (m >> f) & 1;
+    return c;
+}
+__host__ __device__ constexpr int mask_slot(int m, int f)      // index of field f among the set bits
+{
+    int c = 0;
+    for (int g = 0; g < f; g++)
+        c += (m >> g) & 1;
+    return c;
+}
+__host__ __device__ constexpr bool mask_has(int m, int f) { return (m >> f) & 1; }
+
+template <int MASK>
+struct MaskTraits {
+    static constexpr int nf = mask_count(MASK);
+    static constexpr int trec = tvd_test_rec_len(nf);
+    static constexpr bool needs_sinlon = (MASK & ((1 << TVD_GY) | (1 << TVD_GXY) | (1 << TVD_GYY) |
+                                                  (1 << TVD_GYZ))) != 0;
+    static constexpr bool needs_kphi = (MASK & ((1 << TVD_GX) | (1 << TVD_GXX) | (1 << TVD_GXY) |
+                                                (1 << TVD_GXZ))) != 0;
+    static constexpr bool needs_y3 = (MASK & ~(1 << TVD_POTENTIAL)) != 0;
+    static constexpr bool needs_y5 = (MASK >> TVD_GXX) != 0;
+    static constexpr bool needs_dz = (MASK & ((1 << TVD_GZ) | (1 << TVD_GXZ) | (1 << TVD_GYZ) |
+                                              (1 << TVD_GZZ))) != 0;
+    static constexpr bool needs_dx = (MASK & ((1 << TVD_GXX) | (1 << TVD_GXY) | (1 << TVD_GXZ))) != 0;
+    static constexpr bool needs_dy = (MASK & ((1 << TVD_GXY) | (1 << TVD_GYY) | (1 << TVD_GYZ))) != 0;
 };
 
 // per-thread constants of one computation point
@@ -154,13 +184,14 @@ struct Angular {
     double cospsi[2][2];     // [i][j]
     double kphi[2][2];
     double sinlon[2];
-    double clc[2];           // coslatc[j] (tensor dy)
+    double clc[2];           // coslatc[j]
 };
 
-template <int FIELD>
+template <int MASK>
 __device__ __forceinline__ void glq_angular(const PointRegs &pt, const double *__restrict__ g,
                                             Angular &A)
 {
+    typedef MaskTraits<MASK> T;
     const double2 lonc = *reinterpret_cast<const double2 *>(g + 0);
     const double2 sinlatc = *reinterpret_cast<const double2 *>(g + 2);
     const double2 coslatc = *reinterpret_cast<const double2 *>(g + 4);
@@ -168,8 +199,7 @@ __device__ __forceinline__ void glq_angular(const PointRegs &pt, const double *_
     {
         // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
         double s0 = 0.0, s1 = 0.0;
-        trig2<FieldTraits<FIELD>::needs_sinlon>(pt.lon - lonc.x, pt.lon - lonc.y, coslon[0],
-                                                coslon[1], s0, s1);
+        trig2<T::needs_sinlon>(pt.lon - lonc.x, pt.lon - lonc.y, coslon[0], coslon[1], s0, s1);
         A.sinlon[0] = -s0;
         A.sinlon[1] = -s1;
     }
@@ -184,17 +214,19 @@ __device__ __forceinline__ void glq_angular(const PointRegs &pt, const double *_
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             A.cospsi[i][j] = ss[j] + cc[j] * coslon[i];
-            if (FieldTraits<FIELD>::needs_kphi)
+            if (T::needs_kphi)
                 A.kphi[i][j] = pt.coslat * slc[j] - pt.sinlat * A.clc[j] * coslon[i];   // :322
         }
     }
 }
 
-// The radial half: the eight nodes of one piece.
-template <int FIELD>
-__device__ __forceinline__ double glq_radial(const PointRegs &pt, const double *__restrict__ g,
-                                             const Angular &A)
+// The radial half: the eight nodes of one piece, all fields of the mask.  out[slot] receives the
+// piece's contribution to each field (kernel units, reference sign conventions).
+template <int MASK>
+__device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__restrict__ g,
+                                           const Angular &A, double *__restrict__ out)
 {
+    typedef MaskTraits<MASK> T;
     const double2 rc = *reinterpret_cast<const double2 *>(g + 6);
     const double2 rcsq = *reinterpret_cast<const double2 *>(g + 8);
     const double2 w0 = *reinterpret_cast<const double2 *>(g + 10);   // w[0][0], w[0][1]
@@ -203,9 +235,23 @@ __device__ __forceinline__ double glq_radial(const PointRegs &pt, const double *
     const double b[2] = {pt.r_sqr + rcsq.x, pt.r_sqr + rcsq.y};
     const double a[2] = {pt.r2 * rc.x, pt.r2 * rc.y};
     const double rck[2] = {rc.x, rc.y};
-    const double wjk[2][2] = {{w0.x, w0.y}, {w1.x, w1.y}};
+    const double wjk[2][2] = {{w0.x, w0.y}, {w1.x, w1.y}};     // rho_k * kappa_jk * scale
+    // field-specific node weights, same products as the reference's integrands
+    double wx[2][2], wy[2][2];
+    if (mask_has(MASK, TVD_GX) || mask_has(MASK, TVD_GY)) {
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                wx[j][k] = wjk[j][k] * rck[k];                 // kappa*rc[k]*kphi            (:328)
+                wy[j][k] = wx[j][k] * A.clc[j];                // kappa*rc[k]*coslatc*sinlon  (:408)
+            }
+    }
 
-    double sum = 0.0;
+    double sum[T::nf];
+#pragma unroll
+    for (int s = 0; s < T::nf; s++)
+        sum[s] = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
 #pragma unroll
@@ -216,46 +262,76 @@ __device__ __forceinline__ double glq_radial(const PointRegs &pt, const double *
                 const double l_sqr = b[k] - a[k] * cospsi;
                 const double y = rsqrt_fast(l_sqr);
                 const double w = wjk[j][k];
-                if (FIELD == TVD_POTENTIAL) {
-                    sum = fma(w, y, sum);                                  // kappa/sqrt(l_sqr)
-                } else {
-                    const double y3 = y * y * y;
-                    if (FIELD == TVD_GX) {
-                        sum = fma(w * A.kphi[i][j], y3, sum);
-                    } else if (FIELD == TVD_GY) {
-                        sum = fma(w * A.sinlon[i], y3, sum);
-                    } else if (FIELD == TVD_GZ) {
-                        // rc*cospsi - radius (:487); the product is not ill-conditioned enough
-                        // to need the reference's separate rounding (<= 5e-14 relative)
-                        const double dz = fma(rck[k], cospsi, -pt.r);
-                        sum = fma(w * dz, y3, sum);
-                    } else {
-                        // gradient tensor (Fatiando 0.5 integrands, z up)
-                        const double y5 = y3 * y * y;
-                        const double dx = rck[k] * A.kphi[i][j];
-                        const double dy = rck[k] * A.clc[j] * A.sinlon[i];
-                        const double dz = rck[k] * cospsi - pt.r;
-                        double num;
-                        if (FIELD == TVD_GXX) num = 3.0 * (dx * dx) - l_sqr;
-                        else if (FIELD == TVD_GXY) num = 3.0 * dx * dy;
-                        else if (FIELD == TVD_GXZ) num = 3.0 * dx * dz;
-                        else if (FIELD == TVD_GYY) num = 3.0 * (dy * dy) - l_sqr;
-                        else if (FIELD == TVD_GYZ) num = 3.0 * dy * dz;
-                        else num = 3.0 * (dz * dz) - l_sqr;
-                        sum = fma(w * num, y5, sum);
-                    }
+                double y3 = 0.0, y5 = 0.0, dx = 0.0, dy = 0.0, dz = 0.0;
+                if (T::needs_y3)
+                    y3 = y * y * y;
+                if (T::needs_y5)
+                    y5 = y3 * y * y;
+                // rc*cospsi - radius (:487); the product is not ill-conditioned enough to need
+                // the reference's separate rounding (<= 5e-14 relative)
+                if (T::needs_dz)
+                    dz = fma(rck[k], cospsi, -pt.r);
+                if (T::needs_dx)
+                    dx = rck[k] * A.kphi[i][j];
+                if (T::needs_dy)
+                    dy = rck[k] * A.clc[j] * A.sinlon[i];
+                if (mask_has(MASK, TVD_POTENTIAL)) {
+                    double &acc = sum[mask_slot(MASK, TVD_POTENTIAL)];
+                    acc = fma(w, y, acc);                                   // kappa/sqrt(l_sqr)
+                }
+                if (mask_has(MASK, TVD_GX)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GX)];
+                    acc = fma(wx[j][k] * A.kphi[i][j], y3, acc);
+                }
+                if (mask_has(MASK, TVD_GY)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GY)];
+                    acc = fma(wy[j][k] * A.sinlon[i], y3, acc);
+                }
+                if (mask_has(MASK, TVD_GZ)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GZ)];
+                    acc = fma(-(w * dz), y3, acc);                          // z down (:490)
+                }
+                // gradient tensor (Fatiando 0.5 integrands, z up)
+                if (mask_has(MASK, TVD_GXX)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GXX)];
+                    acc = fma(w * (3.0 * (dx * dx) - l_sqr), y5, acc);
+                }
+                if (mask_has(MASK, TVD_GXY)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GXY)];
+                    acc = fma(w * (3.0 * dx * dy), y5, acc);
+                }
+                if (mask_has(MASK, TVD_GXZ)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GXZ)];
+                    acc = fma(w * (3.0 * dx * dz), y5, acc);
+                }
+                if (mask_has(MASK, TVD_GYY)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GYY)];
+                    acc = fma(w * (3.0 * (dy * dy) - l_sqr), y5, acc);
+                }
+                if (mask_has(MASK, TVD_GYZ)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GYZ)];
+                    acc = fma(w * (3.0 * dy * dz), y5, acc);
+                }
+                if (mask_has(MASK, TVD_GZZ)) {
+                    double &acc = sum[mask_slot(MASK, TVD_GZZ)];
+                    acc = fma(w * (3.0 * (dz * dz) - l_sqr), y5, acc);
                 }
             }
         }
     }
-    return sum;
+#pragma unroll
+    for (int s = 0; s < T::nf; s++)
+        out[s] = sum[s];
 }
 
-template <int FIELD, int PPT, int THREADS, int MINBLOCKS>
+template <int MASK, int THREADS, int MINBLOCKS>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 far_sweep(const FarArgs a)
 {
-    __shared__ __align__(16) double s_test[2][TVD_TILE * TVD_TEST_REC];
+    typedef MaskTraits<MASK> T;
+    constexpr int NF = T::nf;
+    constexpr int TREC = T::trec;
+    __shared__ __align__(16) double s_test[2][TVD_TILE * TREC];
     __shared__ __align__(16) double s_glq[2][TVD_TILE * TVD_GLQ_REC];
     __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -268,29 +344,28 @@ far_sweep(const FarArgs a)
         q_end = a.n_pieces;
     const int n_tiles = (int)((q_end - q_begin + TVD_TILE - 1) / TVD_TILE);
 
-    PointRegs pt[PPT];
-    Angular ang[PPT];
-    int64_t pidx[PPT];
-    bool valid[PPT];
-    double acc[PPT];
-#pragma unroll
-    for (int u = 0; u < PPT; u++) {
-        pidx[u] = (int64_t)blockIdx.x * (THREADS * PPT) + u * THREADS + tid;
-        valid[u] = pidx[u] < a.n_points;
-        const int64_t pi = valid[u] ? pidx[u] : 0;     // padding threads shadow point 0
-        pt[u].lon = a.lon[pi];
-        pt[u].sinlat = a.sinlat[pi];
-        pt[u].coslat = a.coslat[pi];
-        pt[u].r = a.radius[pi];
-        pt[u].r_sqr = pt[u].r * pt[u].r;        // radius**2 (:239)
-        pt[u].r2 = 2.0 * pt[u].r;               // 2*radius  (:247)
+    PointRegs pt;
+    Angular ang;
+    const int64_t pidx = (int64_t)blockIdx.x * THREADS + tid;
+    const bool valid = pidx < a.n_points;
+    double acc[NF];
+    {
+        const int64_t pi = valid ? pidx : 0;     // padding threads shadow point 0
+        pt.lon = a.lon[pi];
+        pt.sinlat = a.sinlat[pi];
+        pt.coslat = a.coslat[pi];
+        pt.r = a.radius[pi];
+        pt.r_sqr = pt.r * pt.r;        // radius**2 (:239)
+        pt.r2 = 2.0 * pt.r;            // 2*radius  (:247)
         double sl, cl;
-        sincos(pt[u].lon, &sl, &cl);
-        pt[u].p2x = -pt[u].r2 * (pt[u].coslat * cl);
-        pt[u].p2y = -pt[u].r2 * (pt[u].coslat * sl);
-        pt[u].p2z = -pt[u].r2 * pt[u].sinlat;
-        pt[u].neg_r_sqr = -pt[u].r_sqr;
-        acc[u] = 0.0;
+        sincos(pt.lon, &sl, &cl);
+        pt.p2x = -pt.r2 * (pt.coslat * cl);
+        pt.p2y = -pt.r2 * (pt.coslat * sl);
+        pt.p2z = -pt.r2 * pt.sinlat;
+        pt.neg_r_sqr = -pt.r_sqr;
+#pragma unroll
+        for (int s = 0; s < NF; s++)
+            acc[s] = 0.0;
     }
 
     if (tid == 0) {
@@ -306,10 +381,10 @@ far_sweep(const FarArgs a)
         int64_t nq = q_end - q0;
         if (nq > TVD_TILE)
             nq = TVD_TILE;
-        const uint32_t bt = (uint32_t)(nq * TVD_TEST_REC * sizeof(double));
+        const uint32_t bt = (uint32_t)(nq * TREC * sizeof(double));
         const uint32_t bg = (uint32_t)(nq * TVD_GLQ_REC * sizeof(double));
         mbar_expect_tx(&s_bar[st], bt + bg);
-        bulk_g2s(s_test[st], a.test_rec + q0 * TVD_TEST_REC, bt, &s_bar[st]);
+        bulk_g2s(s_test[st], a.test_rec + q0 * TREC, bt, &s_bar[st]);
         bulk_g2s(s_glq[st], a.glq_rec + q0 * TVD_GLQ_REC, bg, &s_bar[st]);
     };
 
@@ -328,81 +403,113 @@ far_sweep(const FarArgs a)
         const double *tt = s_test[st];
         const double *gg = s_glq[st];
         for (int qi = 0; qi < nq; qi++) {
-            const double2 cxy = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 0);
-            const double2 czk = *reinterpret_cast<const double2 *>(tt + qi * TVD_TEST_REC + 2);
+            const double *trec = tt + qi * TREC;
             const double *grec = gg + qi * TVD_GLQ_REC;
             // record flag: this piece has the lon/lat extent of the previous piece of the tile
             // (a further radial piece of the same tesseroid) -> keep the angular half
             const bool same_extent = reinterpret_cast<const int2 *>(grec + 14)->x != 0;
+            // conservative far-field test: d^2 - thr_f^2 = r^2 + (rt^2 - thr_f^2) - 2 p.c > 0 with
+            // p, c the Cartesian position vectors of the point and the piece centre
+            // (FMA allowed: only the guarded comparison depends on it, see K4)
+            bool far[NF];
+            if (NF == 1) {
+                const double2 cxy = *reinterpret_cast<const double2 *>(trec + 0);
+                const double2 czk = *reinterpret_cast<const double2 *>(trec + 2);
+                double t = fma(pt.p2x, cxy.x, czk.y);
+                t = fma(pt.p2y, cxy.y, t);
+                t = fma(pt.p2z, czk.x, t);
+                far[0] = t > pt.neg_r_sqr;
+            } else {
+                double t = pt.p2x * trec[0];
+                t = fma(pt.p2y, trec[1], t);
+                t = fma(pt.p2z, trec[2], t);
 #pragma unroll
-            for (int u = 0; u < PPT; u++) {
-                // conservative far-field test: d^2 - thr2 = r^2 + (rt^2 - thr2) - 2 p.c > 0 with
-                // p, c the Cartesian position vectors of the point and the piece centre
-                // (FMA allowed: only the guarded comparison depends on it, see K4)
-                double t = fma(pt[u].p2x, cxy.x, czk.y);
-                t = fma(pt[u].p2y, cxy.y, t);
-                t = fma(pt[u].p2z, czk.x, t);
-                const bool far = t > pt[u].neg_r_sqr;
-                const bool defer = !far && valid[u];
+                for (int s = 0; s < NF; s++)
+                    far[s] = (t + trec[3 + s]) > pt.neg_r_sqr;
+            }
+#pragma unroll
+            for (int s = 0; s < NF; s++) {
+                const bool defer = !far[s] && valid;
                 const unsigned m = __ballot_sync(0xffffffffu, defer);
                 if (m) {
                     unsigned long long base = 0;
                     const int leader = __ffs(m) - 1;
                     if (lane == leader)
-                        base = atomicAdd(a.qcount, (unsigned long long)__popc(m));
+                        base = atomicAdd(a.qcount + s, (unsigned long long)__popc(m));
                     base = __shfl_sync(0xffffffffu, base, leader);
                     if (defer) {
                         const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
                         if (idx < a.qcap)
-                            a.queue[idx] = ((unsigned long long)pidx[u] << 32) |
-                                           (unsigned long long)(q0 + qi);
+                            a.queue[(unsigned long long)s * a.qcap + idx] =
+                                ((unsigned long long)pidx << 32) | (unsigned long long)(q0 + qi);
                     }
                 }
-                // every lane evaluates the root GLQ (it contains warp-wide votes); lanes whose
-                // pair was deferred simply drop the value
-                if (!same_extent)
-                    glq_angular<FIELD>(pt[u], grec, ang[u]);
-                const double v = glq_radial<FIELD>(pt[u], grec, ang[u]);
-                if (far)
-                    acc[u] += v;
             }
+            // every lane evaluates the root GLQ (it contains warp-wide votes); lanes whose pair
+            // was deferred simply drop the value
+            if (!same_extent)
+                glq_angular<MASK>(pt, grec, ang);
+            double v[NF];
+            glq_radial<MASK>(pt, grec, ang, v);
+#pragma unroll
+            for (int s = 0; s < NF; s++)
+                if (far[s])
+                    acc[s] += v[s];
         }
         __syncthreads();    // everyone is done with stage st
         if (tid == 0 && tile + 2 < n_tiles)
             issue(tile + 2);
     }
 
+    if (valid) {
 #pragma unroll
-    for (int u = 0; u < PPT; u++)
-        if (valid[u])
-            a.far_out[(int64_t)g * a.n_points + pidx[u]] = acc[u];
+        for (int s = 0; s < NF; s++)
+            a.far_out[((int64_t)s * a.n_groups + g) * a.n_points + pidx] = acc[s];
+    }
 }
 
-template <int FIELD>
-static cudaError_t launch_field(const FarArgs &a, cudaStream_t stream)
+template <int MASK>
+static cudaError_t launch_mask(const FarArgs &a, cudaStream_t stream)
 {
-    constexpr int THREADS = TVD_FAR_THREADS, PPT = TVD_FAR_PPT;
-    dim3 grid((unsigned)((a.n_points + THREADS * PPT - 1) / (THREADS * PPT)), (unsigned)a.n_groups);
-    far_sweep<FIELD, PPT, THREADS, TVD_FAR_MINBLOCKS><<<grid, THREADS, 0, stream>>>(a);
+    constexpr int THREADS = TVD_FAR_THREADS;
+    dim3 grid((unsigned)((a.n_points + THREADS - 1) / THREADS), (unsigned)a.n_groups);
+    far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS><<<grid, THREADS, 0, stream>>>(a);
     tvd_count_launch();
     return cudaGetLastError();
+}
+
+#define TVD_M(f) (1 << (f))
+bool tvd_far_mask_supported(int mask)
+{
+    switch (mask) {
+    case TVD_M(TVD_POTENTIAL): case TVD_M(TVD_GX): case TVD_M(TVD_GY): case TVD_M(TVD_GZ):
+    case TVD_M(TVD_GXX): case TVD_M(TVD_GXY): case TVD_M(TVD_GXZ): case TVD_M(TVD_GYY):
+    case TVD_M(TVD_GYZ): case TVD_M(TVD_GZZ):
+    case TVD_MASK_V_GZ_GZZ: case TVD_MASK_V_G: case TVD_MASK_G: case TVD_MASK_TENSOR:
+        return true;
+    }
+    return false;
 }
 
 cudaError_t tvd_launch_far(const FarArgs &a, cudaStream_t stream)
 {
     if (a.n_points == 0 || a.n_pieces == 0)
         return cudaSuccess;
-    switch (a.field) {
-    case TVD_POTENTIAL: return launch_field<TVD_POTENTIAL>(a, stream);
-    case TVD_GX: return launch_field<TVD_GX>(a, stream);
-    case TVD_GY: return launch_field<TVD_GY>(a, stream);
-    case TVD_GZ: return launch_field<TVD_GZ>(a, stream);
-    case TVD_GXX: return launch_field<TVD_GXX>(a, stream);
-    case TVD_GXY: return launch_field<TVD_GXY>(a, stream);
-    case TVD_GXZ: return launch_field<TVD_GXZ>(a, stream);
-    case TVD_GYY: return launch_field<TVD_GYY>(a, stream);
-    case TVD_GYZ: return launch_field<TVD_GYZ>(a, stream);
-    case TVD_GZZ: return launch_field<TVD_GZZ>(a, stream);
+    switch (a.mask) {
+    case TVD_M(TVD_POTENTIAL): return launch_mask<TVD_M(TVD_POTENTIAL)>(a, stream);
+    case TVD_M(TVD_GX): return launch_mask<TVD_M(TVD_GX)>(a, stream);
+    case TVD_M(TVD_GY): return launch_mask<TVD_M(TVD_GY)>(a, stream);
+    case TVD_M(TVD_GZ): return launch_mask<TVD_M(TVD_GZ)>(a, stream);
+    case TVD_M(TVD_GXX): return launch_mask<TVD_M(TVD_GXX)>(a, stream);
+    case TVD_M(TVD_GXY): return launch_mask<TVD_M(TVD_GXY)>(a, stream);
+    case TVD_M(TVD_GXZ): return launch_mask<TVD_M(TVD_GXZ)>(a, stream);
+    case TVD_M(TVD_GYY): return launch_mask<TVD_M(TVD_GYY)>(a, stream);
+    case TVD_M(TVD_GYZ): return launch_mask<TVD_M(TVD_GYZ)>(a, stream);
+    case TVD_M(TVD_GZZ): return launch_mask<TVD_M(TVD_GZZ)>(a, stream);
+    case TVD_MASK_V_GZ_GZZ: return launch_mask<TVD_MASK_V_GZ_GZZ>(a, stream);
+    case TVD_MASK_V_G: return launch_mask<TVD_MASK_V_G>(a, stream);
+    case TVD_MASK_G: return launch_mask<TVD_MASK_G>(a, stream);
+    case TVD_MASK_TENSOR: return launch_mask<TVD_MASK_TENSOR>(a, stream);
     }
     return cudaErrorInvalidValue;
 }

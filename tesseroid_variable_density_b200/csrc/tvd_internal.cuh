@@ -15,8 +15,16 @@
 #define TVD_NODE 0.577350269189625731058868041146   // _tesseroid.pyx:27-28
 
 // Far-field record sizes (doubles per radial piece); see DESIGN.md "data layout".
-#define TVD_TEST_REC 4
+// test record: cx cy cz K_0 .. K_{nf-1}, padded to an even number of doubles (16-byte records)
+__host__ __device__ constexpr int tvd_test_rec_len(int nf) { return ((3 + nf) + 1) / 2 * 2; }
 #define TVD_GLQ_REC 16
+#define TVD_MAX_FUSED 6                     // fields per fused sweep
+// fused field sets the sweep is compiled for (besides the ten single fields)
+#define TVD_MASK_V_GZ_GZZ ((1 << TVD_POTENTIAL) | (1 << TVD_GZ) | (1 << TVD_GZZ))
+#define TVD_MASK_V_G ((1 << TVD_POTENTIAL) | (1 << TVD_GX) | (1 << TVD_GY) | (1 << TVD_GZ))
+#define TVD_MASK_G ((1 << TVD_GX) | (1 << TVD_GY) | (1 << TVD_GZ))
+#define TVD_MASK_TENSOR ((1 << TVD_GXX) | (1 << TVD_GXY) | (1 << TVD_GXZ) | (1 << TVD_GYY) | \
+                         (1 << TVD_GYZ) | (1 << TVD_GZZ))
 #define TVD_TILE 64                         // pieces per shared-memory tile
 // far-field sweep launch shape: threads per block, points per thread, resident blocks per SM
 #ifndef TVD_FAR_THREADS
@@ -191,21 +199,29 @@ cudaError_t tvd_launch_scan(const int32_t *d_counts, int64_t *d_offsets, int64_t
                             cudaStream_t stream);   // exclusive scan, d_offsets[n] = total
 cudaError_t tvd_launch_k1_emit(const PieceTable &t, const int64_t *d_offsets, double delta,
                                int has_delta, cudaStream_t stream);
-// K4: per-piece root records for the far-field sweep of one (field, ratio)
-cudaError_t tvd_launch_pack(int field, const PieceTable &t, double ratio, double *d_test,
-                            double *d_glq, cudaStream_t stream);
+// K4: per-piece root records for the far-field sweep.  The GLQ records depend on the model
+// only; the test records on the distance-size ratio of each field of the sweep.
+cudaError_t tvd_launch_pack_glq(const PieceTable &t, double *d_glq, double *d_geom,
+                                cudaStream_t stream);
+struct RatioList {
+    int nf;
+    double ratio[TVD_MAX_FUSED];
+};
+cudaError_t tvd_launch_pack_test(const PieceTable &t, const double *d_geom, RatioList ratios,
+                                 double *d_test, cudaStream_t stream);
 // Phase A: far-field sweep
+bool tvd_far_mask_supported(int mask);
 struct FarArgs {
-    int field;
+    int mask;                        // bit f set: tvd_field f is computed
     int64_t n_points;
     const double *lon, *sinlat, *coslat, *radius;
     int64_t n_pieces;
     const double *test_rec, *glq_rec;
     int n_groups;
     int64_t pieces_per_group;
-    double *far_out;                 // [n_groups][n_points]
-    unsigned long long *queue;       // near-field pairs: (point << 32) | piece
-    unsigned long long *qcount;
+    double *far_out;                 // [nf][n_groups][n_points]
+    unsigned long long *queue;       // [nf][qcap] near-field pairs: (point << 32) | piece
+    unsigned long long *qcount;      // [nf]
     unsigned long long qcap;
 };
 cudaError_t tvd_launch_far(const FarArgs &a, cudaStream_t stream);

@@ -245,17 +245,20 @@ cudaError_t tvd_launch_scan(const int32_t *d_counts, int64_t *d_offsets, int64_t
 // ---------------------------------------------------------------------------------------------
 // K4: root records
 // ---------------------------------------------------------------------------------------------
-// test record  [4]: cx cy cz (Cartesian centre of the piece)  rt^2 - thr2
-//   thr2 is the conservative far-field threshold on the squared centre distance, see
-//   tvd_far.cu; pairs that do not clear it are re-examined with the literal test.
 // glq record  [16]: lonc0 lonc1 sinlatc0 sinlatc1 coslatc0 coslatc1 rc0 rc1 rc0^2 rc1^2
-//                   w00 w01 w10 w11 (w[j][k])  same-extent flag (int64)  (pad)
+//                   w00 w01 w10 w11 (w[j][k] = rho_k * kappa_jk * scale)
+//                   same-extent flag (int64)  (pad)
+// geometry     [5]: cx cy cz (Cartesian centre of the piece)  rt^2  max(Llon, Llat)
+// test record: cx cy cz K_0 .. K_{nf-1} with K_f = rt^2 - thr2(ratio_f); thr2 is the conservative
+//   far-field threshold on the squared centre distance, see tvd_far.cu; pairs that do not clear
+//   it are re-examined with the literal test.
+#define TVD_GEOM_REC 5
 __global__ void __launch_bounds__(128)
-k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bounds,
-              const int32_t *__restrict__ tess_kind, const double *__restrict__ tess_params,
-              const double *__restrict__ ptop, const double *__restrict__ pbottom,
-              const int32_t *__restrict__ parent, double ratio, double *__restrict__ test_rec,
-              double *__restrict__ glq_rec)
+k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
+            const int32_t *__restrict__ tess_kind, const double *__restrict__ tess_params,
+            const double *__restrict__ ptop, const double *__restrict__ pbottom,
+            const int32_t *__restrict__ parent, double *__restrict__ glq_rec,
+            double *__restrict__ geom)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_pieces)
@@ -279,18 +282,12 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
     const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * dd_cos(TVD_D2R * (e - w)));
     const double Llat = rtop * acos(dd_sin(TVD_D2R * n) * dd_sin(TVD_D2R * s) +
                                     dd_cos(TVD_D2R * n) * dd_cos(TVD_D2R * s));
-    // Conservative far-field threshold.  The literal test (divisions, :135,140) splits iff
-    // d <= ratio*Llon or d <= ratio*Llat (NaN sizes never split).  The sweep evaluates
-    // d^2 = r^2 + rt^2 - 2 p.c from Cartesian position vectors with an absolute error far below
-    // 1 m^2, so d2 > thr^2*(1+1e-9) + 2 guarantees that the literal test says "no split";
-    // everything else is deferred to the literal walk.
-    const double thr = fmax(ratio * Llon, ratio * Llat);    // fmax ignores a single NaN
-    const double thr2 = thr * thr * (1.0 + 1e-9) + 2.0;     // NaN if both sizes are NaN
-    double *tr = test_rec + TVD_TEST_REC * q;
-    tr[0] = rt * (coslatt * dd_cos(lont));     // centre of the piece, geocentric Cartesian
-    tr[1] = rt * (coslatt * dd_sin(lont));
-    tr[2] = rt * sinlatt;
-    tr[3] = rt * rt - thr2;                 // a NaN threshold defers every pair of the piece
+    double *gm = geom + TVD_GEOM_REC * q;
+    gm[0] = rt * (coslatt * dd_cos(lont));     // centre of the piece, geocentric Cartesian
+    gm[1] = rt * (coslatt * dd_sin(lont));
+    gm[2] = rt * sinlatt;
+    gm[3] = rt * rt;
+    gm[4] = fmax(Llon, Llat);                  // fmax ignores a single NaN (a NaN size never splits)
 
     // scale_nodes (_tesseroid.pyx:162-175)
     const double dlon = e - w, dlat = n - s, dr = top - bottom;
@@ -325,14 +322,7 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const double kappa = rcsq[k] * coslatc[j];          // :248
-            double wjk = dens[k] * kappa * scale;
-            switch (field) {
-            case TVD_GX: wjk = wjk * rc[k]; break;                  // kappa*rc*kphi/l^3   (:328)
-            case TVD_GY: wjk = wjk * rc[k] * coslatc[j]; break;     // kappa*rc*coslatc*sinlon/l^3 (:408)
-            case TVD_GZ: wjk = -wjk; break;                         // z down (:490)
-            default: break;
-            }
-            g[10 + 2 * j + k] = wjk;
+            g[10 + 2 * j + k] = dens[k] * kappa * scale;
         }
     }
     // flag (as a 64-bit integer): same lon/lat extent as the previous piece of the same tile,
@@ -342,16 +332,55 @@ k4_pack_roots(int field, int64_t n_pieces, const double *__restrict__ tess_bound
     g[15] = 0.0;
 }
 
-cudaError_t tvd_launch_pack(int field, const PieceTable &t, double ratio, double *d_test,
-                            double *d_glq, cudaStream_t stream)
+// Conservative far-field threshold.  The literal test (divisions, :135,140) splits iff
+// d <= ratio*Llon or d <= ratio*Llat (NaN sizes never split).  The sweep evaluates
+// d^2 = r^2 + rt^2 - 2 p.c from Cartesian position vectors with an absolute error far below
+// 1 m^2, so d2 > thr^2*(1+1e-9) + 2 guarantees that the literal test says "no split";
+// everything else is deferred to the literal walk.
+__global__ void __launch_bounds__(128)
+k4_pack_test(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios,
+             double *__restrict__ test_rec)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pieces)
+        return;
+    const int trec = tvd_test_rec_len(ratios.nf);
+    const double *gm = geom + TVD_GEOM_REC * q;
+    double *tr = test_rec + (int64_t)trec * q;
+    tr[0] = gm[0];
+    tr[1] = gm[1];
+    tr[2] = gm[2];
+    for (int f = 0; f < ratios.nf; f++) {
+        const double thr = ratios.ratio[f] * gm[4];             // = max(ratio*Llon, ratio*Llat)
+        const double thr2 = thr * thr * (1.0 + 1e-9) + 2.0;     // NaN if both sizes are NaN
+        tr[3 + f] = gm[3] - thr2;       // a NaN threshold defers every pair of the piece
+    }
+    for (int f = 3 + ratios.nf; f < trec; f++)
+        tr[f] = 0.0;
+}
+
+cudaError_t tvd_launch_pack_glq(const PieceTable &t, double *d_glq, double *d_geom,
+                                cudaStream_t stream)
 {
     if (t.n_pieces == 0)
         return cudaSuccess;
     const int threads = 128;
     const unsigned blocks = (unsigned)((t.n_pieces + threads - 1) / threads);
-    k4_pack_roots<<<blocks, threads, 0, stream>>>(field, t.n_pieces, t.tess_bounds, t.tess_kind,
-                                                  t.tess_params, t.top, t.bottom, t.parent, ratio,
-                                                  d_test, d_glq);
+    k4_pack_glq<<<blocks, threads, 0, stream>>>(t.n_pieces, t.tess_bounds, t.tess_kind,
+                                                t.tess_params, t.top, t.bottom, t.parent, d_glq,
+                                                d_geom);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t tvd_launch_pack_test(const PieceTable &t, const double *d_geom, RatioList ratios,
+                                 double *d_test, cudaStream_t stream)
+{
+    if (t.n_pieces == 0)
+        return cudaSuccess;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((t.n_pieces + threads - 1) / threads);
+    k4_pack_test<<<blocks, threads, 0, stream>>>(t.n_pieces, d_geom, ratios, d_test);
     tvd_count_launch();
     return cudaGetLastError();
 }

@@ -172,6 +172,94 @@ def forward_raw(field, lon_rad, sinlat, coslat, radius, prepared, ratio, njobs=1
     return result
 
 
+def fused_supported(fields):
+    """True if `fields` (names) can be evaluated in one fused far-field sweep."""
+    lib = _lib.load()
+    ids = (C.c_int * len(fields))(*[_lib.FIELDS[f] for f in fields])
+    return bool(lib.tvd_fused_supported(len(fields), ids))
+
+
+def forward_raw_fused(fields, lon_rad, sinlat, coslat, radius, prepared, ratios, njobs=1,
+                      devices=None, return_stats=False):
+    """
+    Several fields in one far-field sweep (``tvd_forward_fused``): ``{field: array}`` in kernel
+    units; each field's values are bit-identical to a separate :func:`forward_raw` call.
+    """
+    lib = _lib.load()
+    lon_rad, sinlat = _lib.as_f64(lon_rad), _lib.as_f64(sinlat)
+    coslat, radius = _lib.as_f64(coslat), _lib.as_f64(radius)
+    n, nf = lon_rad.size, len(fields)
+    results = np.zeros((nf, n))
+    stats = np.zeros((nf, _lib.NSTATS), dtype=np.int64)
+    ids = (C.c_int * nf)(*[_lib.FIELDS[f] for f in fields])
+    rat = np.ascontiguousarray([float(r) for r in ratios], dtype=np.float64)
+    if devices is not None:
+        dev_ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        ndev = len(devices)
+    else:
+        dev_ids = None
+        ndev = int(njobs)
+        avail = lib.tvd_device_count()
+        if avail > 0 and ndev > avail:
+            ndev = avail
+    rc = lib.tvd_forward_fused(nf, ids, _lib.ptr_f64(rat), prepared.handle, n,
+                               _lib.ptr_f64(lon_rad), _lib.ptr_f64(sinlat), _lib.ptr_f64(coslat),
+                               _lib.ptr_f64(radius), int(STACK_SIZE), ndev, dev_ids,
+                               _lib.ptr_f64(results), _lib.ptr_i64(stats))
+    _lib.check(rc, "tvd_forward_fused")
+    if np.any(stats[:, 3] != 0):
+        warnings.warn(_WARNING_MSG, RuntimeWarning)
+    out = {f: results[i] for i, f in enumerate(fields)}
+    if return_stats:
+        return out, {f: dict(zip(_lib.STAT_NAMES, (int(s) for s in stats[i])))
+                     for i, f in enumerate(fields)}
+    return out
+
+
+_UNITS = {'potential': G, 'gx': SI2MGAL*G, 'gy': SI2MGAL*G, 'gz': SI2MGAL*G}
+_DEFAULT_RATIO = {'potential': RATIO_V, 'gx': RATIO_G, 'gy': RATIO_G, 'gz': RATIO_G}
+for _f in ('gxx', 'gxy', 'gxz', 'gyy', 'gyz', 'gzz'):
+    _UNITS[_f] = SI2EOTVOS*G
+    _DEFAULT_RATIO[_f] = RATIO_GG
+
+
+def fields(names, lon, lat, height, model, dens=None, ratios=None, njobs=1, pool=None,
+           delta=DELTA, devices=None):
+    """
+    Several fields of one model on the same points, e.g.
+    ``fields(["potential", "gz", "gzz"], lon, lat, height, model)`` -> ``{name: array}``.
+
+    The reference computes one field per call, each a full pass over points x tesseroids
+    (tesseroid.py:377,435,493,556).  Here the model is flattened and discretised once, and field
+    sets the far-field sweep is compiled for (see ``include/tvd.h``) share one sweep; other sets
+    run field by field.  Values are bit-identical to the single-field functions; ``ratios``
+    defaults to each field's own default (1 / 2.5 / 8).
+    """
+    names = list(names)
+    if ratios is None:
+        ratios = [_DEFAULT_RATIO[f] for f in names]
+    lon, lat, height = np.asarray(lon), np.asarray(lat), np.asarray(height)
+    for r in ratios:
+        _check_input(lon, lat, height, model, r, njobs, pool)
+    shape = lon.shape
+    cc = _convert_coords(np.asarray(lon, dtype=np.float64).ravel(),
+                         np.asarray(lat, dtype=np.float64).ravel(),
+                         np.asarray(height, dtype=np.float64).ravel())
+    own = not isinstance(model, PreparedModel)
+    prepared = PreparedModel(model, dens=dens, delta=delta,
+                             device=(devices[0] if devices else 0)) if own else model
+    try:
+        if len(names) > 1 and fused_supported(names):
+            raw = forward_raw_fused(names, *cc, prepared, ratios, njobs=njobs, devices=devices)
+        else:
+            raw = {f: forward_raw(f, *cc, prepared, r, njobs=njobs, devices=devices)
+                   for f, r in zip(names, ratios)}
+    finally:
+        if own:
+            prepared.close()
+    return {f: (raw[f] * _UNITS[f]).reshape(shape) for f in names}
+
+
 def _dispatcher(field, lon, lat, height, model, **kwargs):
     """Counterpart of the reference's ``_dispatcher`` + ``_forward_model``
     (tesseroid.py:164-234): one preprocessing call and one batched forward call."""

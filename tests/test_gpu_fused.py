@@ -1,0 +1,69 @@
+"""Fused multi-field sweeps: same bits as the single-field calls."""
+import numpy as np
+import pytest
+
+import cases
+from tesseroid_variable_density_b200 import gridder, tesseroid
+from tesseroid_variable_density_b200.tesseroid import (PreparedModel, _convert_coords, forward_raw,
+                                                       forward_raw_fused, fused_supported)
+
+pytestmark = pytest.mark.gpu
+
+SETS = [
+    ["potential", "gz", "gzz"],
+    ["potential", "gx", "gy", "gz"],
+    ["gx", "gy", "gz"],
+    ["gxx", "gxy", "gxz", "gyy", "gyz", "gzz"],
+    ["gzz", "potential", "gz"],           # caller order differs from slot order
+]
+
+
+@pytest.mark.parametrize("names", SETS, ids=["-".join(s) for s in SETS])
+@pytest.mark.parametrize("grid", ["global2km", "260km"])
+def test_fused_equals_single_field_calls(names, grid):
+    mesh = cases.sine_case(1e5, 2)[0]
+    lats, lons, heights = cases.GRIDS[grid]()
+    cc = _convert_coords(lons, lats, heights)
+    pm = PreparedModel(mesh, delta=0.1)
+    ratios = [cases.DEFAULT_RATIO[f] for f in names]
+    assert fused_supported(names)
+    fused, fstats = forward_raw_fused(names, *cc, pm, ratios, return_stats=True)
+    for f, r in zip(names, ratios):
+        single, sstats = forward_raw(f, *cc, pm, r, return_stats=True)
+        assert np.array_equal(fused[f], single), f
+        assert fstats[f] == sstats, f
+    pm.close()
+
+
+def test_fused_regional_with_near_field(oracle_lib):
+    from test_gpu_parity import regional_model
+    from tesseroid_variable_density_b200.model import flatten_model
+    tm = regional_model(nlat=20, nlon=24)
+    lats, lons, heights = gridder.regular((-39.9, -39.1, 288.1, 289.1), (25, 25), z=2000.)
+    cc = _convert_coords(lons, lats, heights)
+    pm = PreparedModel(tm, delta=0.1)
+    names = ["potential", "gz", "gzz"]
+    fused, st = forward_raw_fused(names, *cc, pm, [1, 2.5, 8], return_stats=True)
+    pm.close()
+    assert st["gzz"]["near_pairs"] > st["gz"]["near_pairs"] > st["potential"]["near_pairs"] > 0
+    flat = flatten_model(tm)
+    for f, r, tol in (("potential", 1, 1e-9), ("gz", 2.5, 1e-9), ("gzz", 8, 1e-6)):
+        o, so = oracle_lib.forward(f, flat.bounds, flat.kind, flat.params, 0.1, r, *cc, n_threads=8)
+        assert np.max(np.abs(fused[f] - o)) <= tol * np.max(np.abs(o)), f
+        assert all(st[f][k] == so[k] for k in ("nodes", "leaves", "splits")), f
+
+
+def test_fields_api():
+    mesh, _, exact = cases.exponential_case(1e4, 10)
+    lats, lons, heights = cases.GRIDS["260km"]()
+    out = tesseroid.fields(["potential", "gz", "gzz"], lons, lats, heights, mesh, delta=0.1)
+    assert np.array_equal(out["gz"], tesseroid.gz(lons, lats, heights, mesh, delta=0.1))
+    assert np.array_equal(out["gzz"], tesseroid.gzz(lons, lats, heights, mesh, delta=0.1))
+    assert np.array_equal(out["potential"], tesseroid.potential(lons, lats, heights, mesh, delta=0.1))
+    ex = exact(heights[0])
+    for f in out:
+        assert cases.percent_difference(out[f], ex[f]) <= 0.1
+    # a set that is not compiled in falls back to field-by-field evaluation
+    assert not fused_supported(["gx", "gzz"])
+    out = tesseroid.fields(["gx", "gzz"], lons, lats, heights, mesh, delta=0.1)
+    assert np.array_equal(out["gzz"], tesseroid.gzz(lons, lats, heights, mesh, delta=0.1))
