@@ -161,6 +161,18 @@ int tvd_forward_fused(int n_fields, const int *fields, const double *ratios, tvd
                       const double *coslat, const double *radius, int stack_size, int n_devices,
                       const int *device_ids, double *results, int64_t *stats);
 
+/*
+ * Sensitivity (Jacobian) mode: the contribution of every input tesseroid to every point,
+ * jac[t][p], instead of their sum.  The reference builds such matrices one
+ * column at a time with `field(lon, lat, height, [tesseroid_t], dens=1)`
+ * ("Use this, e.g., for sensitivity matrix building", tesseroid.py:347-349); row t here is
+ * bit-identical to that call.  Single device; jac is a HOST buffer [n_tess][n_points], kernel
+ * units.  Device memory needed: (n_pieces + n_tess) * n_points * 8 bytes.
+ */
+int tvd_sensitivity(int field, tvd_model *model, int64_t n_points, const double *lon_rad,
+                    const double *sinlat, const double *coslat, const double *radius,
+                    double ratio, int stack_size, int device, double *jac, int64_t *stats);
+
 /* 1 if tvd_forward_fused accepts this set of fields, else 0. */
 int tvd_fused_supported(int n_fields, const int *fields);
 

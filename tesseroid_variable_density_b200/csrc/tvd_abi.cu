@@ -78,7 +78,7 @@ struct DeviceCtx {
     double packed_ratio[TVD_MAX_FUSED] = {0};
     Buf test_rec, glq_rec, geom;
     Buf far_out, queue, keys_sorted, pair_result, sort_temp, counters;
-    Buf pts, result, counts;
+    Buf pts, result, counts, jac_pieces, jac_out;
     unsigned long long qcap_hint = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -101,6 +101,7 @@ static void free_table(PieceTable &t)
     cudaFree(t.tess_kind);
     cudaFree(t.tess_params);
     cudaFree(t.tess_npieces);
+    cudaFree(t.tess_offset);
     cudaFree(t.top);
     cudaFree(t.bottom);
     cudaFree(t.parent);
@@ -125,6 +126,8 @@ static void free_ctx(DeviceCtx *c)
     c->pts.release();
     c->result.release();
     c->counts.release();
+    c->jac_pieces.release();
+    c->jac_out.release();
     if (c->ev0)
         cudaEventDestroy(c->ev0);
     if (c->ev1)
@@ -210,6 +213,15 @@ static int get_ctx(tvd_model *m, int device, DeviceCtx **out)
         if (e == cudaSuccess && m->n_tess > 0)
             e = cudaMemcpy(c->tab.tess_npieces, m->h_npieces.data(),
                            m->n_tess * sizeof(int32_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            std::vector<int64_t> off((size_t)m->n_tess + 1, 0);
+            for (int64_t i = 0; i < m->n_tess; i++)
+                off[i + 1] = off[i] + m->h_npieces[i];
+            e = cudaMalloc(&c->tab.tess_offset, off.size() * sizeof(int64_t));
+            if (e == cudaSuccess)
+                e = cudaMemcpy(c->tab.tess_offset, off.data(), off.size() * sizeof(int64_t),
+                               cudaMemcpyHostToDevice);
+        }
         if (e != cudaSuccess) {
             g_last_error = std::string("piece table replication failed: ") + cudaGetErrorString(e);
             rc = (int)e;
@@ -360,7 +372,8 @@ extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int3
     int64_t *d_offsets = nullptr;
     auto cleanup_tmp = [&]() {
         cudaFree(d_status);
-        cudaFree(d_offsets);
+        if (c->tab.tess_offset != d_offsets)
+            cudaFree(d_offsets);
     };
 #define MODEL_TRY(expr)                                                                  \
     do {                                                                                 \
@@ -401,6 +414,7 @@ extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int3
         return fail(rc);
     }
     MODEL_TRY(tvd_launch_k1_emit(c->tab, d_offsets, m->delta, m->has_delta, c->stream));
+    c->tab.tess_offset = d_offsets;     // owned by the piece table from here on
     m->h_top.resize(total);
     m->h_bottom.resize(total);
     m->h_parent.resize(total);
@@ -494,7 +508,8 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
                         const double *d_lon, const double *d_sinlat, const double *d_coslat,
                         const double *d_radius, int stack_size, int n_groups,
                         double *const *d_results /*[nf]*/, int64_t *stats /*[nf][TVD_NSTATS]*/,
-                        int32_t *d_leaf_counts, cudaStream_t stream)
+                        int32_t *d_leaf_counts, cudaStream_t stream,
+                        double *d_jac_out = nullptr /*sensitivity mode: [n_tess][P], nf == 1*/)
 {
     const int64_t Q = m->n_pieces;
     const int nf = fs.nf;
@@ -540,6 +555,8 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
             c->packed_ratio[f] = fs.ratio[f];
     }
     CUDA_TRY(c->far_out.reserve((size_t)nf * n_groups * P * sizeof(double)));
+    if (d_jac_out)
+        CUDA_TRY(c->jac_pieces.reserve((size_t)Q * P * sizeof(double)));
     const int n_cnt = 8 + 8 * TVD_MAX_FUSED;
     CUDA_TRY(c->counters.reserve(n_cnt * sizeof(unsigned long long)));
     unsigned long long qcap = c->qcap_hint;
@@ -574,6 +591,7 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
         fa.queue = c->queue.as<unsigned long long>();
         fa.qcount = d_cnt;
         fa.qcap = qcap;
+        fa.jac = d_jac_out ? c->jac_pieces.as<double>() : nullptr;
         CUDA_TRY(cudaEventRecord(c->ev0, stream));
         CUDA_TRY(tvd_launch_far(fa, stream));
         CUDA_TRY(cudaEventRecord(c->ev1, stream));
@@ -634,10 +652,14 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
             na.n_points = P;
             CUDA_TRY(tvd_launch_near(na, stream));
         }
-        CUDA_TRY(tvd_launch_combine(P, n_groups,
-                                    c->far_out.as<double>() + (size_t)f * n_groups * P,
-                                    (int64_t)n, d_keys, c->pair_result.as<double>(),
-                                    d_results[f], stream));
+        if (d_jac_out)
+            CUDA_TRY(tvd_launch_jac_reduce(c->tab, P, c->jac_pieces.as<double>(), (int64_t)n,
+                                           d_keys, c->pair_result.as<double>(), d_jac_out, stream));
+        else
+            CUDA_TRY(tvd_launch_combine(P, n_groups,
+                                        c->far_out.as<double>() + (size_t)f * n_groups * P,
+                                        (int64_t)n, d_keys, c->pair_result.as<double>(),
+                                        d_results[f], stream));
         // keys_sorted / pair_result are reused by the next field: the stream orders the kernels
     }
     unsigned long long h_cnt[8 + 8 * TVD_MAX_FUSED];
@@ -878,4 +900,48 @@ extern "C" int tvd_forward_fused(int n_fields, const int *fields, const double *
 {
     return forward_host(n_fields, fields, ratios, m, n_points, lon, sinlat, coslat, radius,
                         stack_size, n_devices, device_ids, results, stats, nullptr);
+}
+
+extern "C" int tvd_sensitivity(int field, tvd_model *m, int64_t n_points, const double *lon,
+                               const double *sinlat, const double *coslat, const double *radius,
+                               double ratio, int stack_size, int device, double *jac,
+                               int64_t *stats)
+{
+    g_last_error.clear();
+    if (!m || n_points < 0 || (n_points > 0 && (!lon || !sinlat || !coslat || !radius || !jac)))
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_sensitivity: bad argument");
+    FieldSet fs;
+    int order[1];
+    int rc = make_field_set(1, &field, &ratio, fs, order);
+    if (rc)
+        return rc;
+    if (device < 0 || device >= tvd_device_count())
+        return set_error(TVD_ERR_NO_DEVICE, "tvd_sensitivity: no such CUDA device (no CPU fallback)");
+    if (stats)
+        memset(stats, 0, TVD_NSTATS * sizeof(int64_t));
+    const int64_t P = n_points, T = m->n_tess;
+    if (P == 0 || T == 0)
+        return TVD_OK;
+    DeviceCtx *c = nullptr;
+    rc = get_ctx(m, device, &c);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(c->pts.reserve((size_t)P * 4 * sizeof(double)));
+    CUDA_TRY(c->jac_out.reserve((size_t)T * P * sizeof(double)));
+    double *d_pts = c->pts.as<double>();
+    const double *src[4] = {lon, sinlat, coslat, radius};
+    for (int k = 0; k < 4; k++)
+        CUDA_TRY(cudaMemcpyAsync(d_pts + (size_t)k * P, src[k], P * sizeof(double),
+                                 cudaMemcpyHostToDevice, c->stream));
+    double *res[1] = {nullptr};
+    rc = forward_core(m, c, fs, P, d_pts, d_pts + P, d_pts + 2 * P, d_pts + 3 * P, stack_size, 1,
+                      res, stats, nullptr, c->stream, c->jac_out.as<double>());
+    if (rc)
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(jac, c->jac_out.p, (size_t)T * P * sizeof(double),
+                             cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TVD_OK;
 }

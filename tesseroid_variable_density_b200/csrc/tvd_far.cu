@@ -324,7 +324,7 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
         out[s] = sum[s];
 }
 
-template <int MASK, int THREADS, int MINBLOCKS>
+template <int MASK, int THREADS, int MINBLOCKS, bool JAC>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 far_sweep(const FarArgs a)
 {
@@ -451,17 +451,24 @@ far_sweep(const FarArgs a)
                 glq_angular<MASK>(pt, grec, ang);
             double v[NF];
             glq_radial<MASK>(pt, grec, ang, v);
+            if (JAC) {
+                // sensitivity mode: one value per (piece, point); NaN marks a deferred pair
+                if (valid)
+                    a.jac[(q0 + qi) * a.n_points + pidx] =
+                        far[0] ? v[0] : __longlong_as_double(0x7ff8000000000000ll);
+            } else {
 #pragma unroll
-            for (int s = 0; s < NF; s++)
-                if (far[s])
-                    acc[s] += v[s];
+                for (int s = 0; s < NF; s++)
+                    if (far[s])
+                        acc[s] += v[s];
+            }
         }
         __syncthreads();    // everyone is done with stage st
         if (tid == 0 && tile + 2 < n_tiles)
             issue(tile + 2);
     }
 
-    if (valid) {
+    if (valid && !JAC) {
 #pragma unroll
         for (int s = 0; s < NF; s++)
             a.far_out[((int64_t)s * a.n_groups + g) * a.n_points + pidx] = acc[s];
@@ -473,7 +480,14 @@ static cudaError_t launch_mask(const FarArgs &a, cudaStream_t stream)
 {
     constexpr int THREADS = TVD_FAR_THREADS;
     dim3 grid((unsigned)((a.n_points + THREADS - 1) / THREADS), (unsigned)a.n_groups);
-    far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS><<<grid, THREADS, 0, stream>>>(a);
+    if (a.jac != nullptr) {
+        if constexpr (mask_count(MASK) == 1)
+            far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, true><<<grid, THREADS, 0, stream>>>(a);
+        else
+            return cudaErrorInvalidValue;
+    } else {
+        far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, false><<<grid, THREADS, 0, stream>>>(a);
+    }
     tvd_count_launch();
     return cudaGetLastError();
 }

@@ -186,6 +186,7 @@ struct PieceTable {
     int32_t *tess_kind = nullptr;    // [n_tess]
     double *tess_params = nullptr;   // [n_tess][TVD_NPAR]
     int32_t *tess_npieces = nullptr; // [n_tess]
+    int64_t *tess_offset = nullptr;  // [n_tess + 1] first piece of each tesseroid
     double *top = nullptr;           // [n_pieces]
     double *bottom = nullptr;        // [n_pieces]
     int32_t *parent = nullptr;       // [n_pieces]
@@ -223,8 +224,14 @@ struct FarArgs {
     unsigned long long *queue;       // [nf][qcap] near-field pairs: (point << 32) | piece
     unsigned long long *qcount;      // [nf]
     unsigned long long qcap;
+    double *jac;                     // sensitivity mode (single field): [n_pieces][n_points],
+                                     // NaN marks a deferred pair; far_out is not written
 };
 cudaError_t tvd_launch_far(const FarArgs &a, cudaStream_t stream);
+// sensitivity mode: rows of pieces -> rows of tesseroids, near-field terms added in piece order
+cudaError_t tvd_launch_jac_reduce(const PieceTable &t, int64_t n_points, const double *jac_pieces,
+                                  int64_t n_pairs, const unsigned long long *keys,
+                                  const double *pair_result, double *jac_out, cudaStream_t stream);
 // sort of the near-field pair keys (CUB radix sort; bookkeeping, tvd_sort.cu)
 cudaError_t tvd_sort_keys(void *d_temp, size_t &temp_bytes, const unsigned long long *in,
                           unsigned long long *out, int64_t n, int end_bit, cudaStream_t stream);

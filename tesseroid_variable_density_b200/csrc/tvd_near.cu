@@ -299,3 +299,66 @@ cudaError_t tvd_launch_combine(int64_t n_points, int n_groups, const double *far
     tvd_count_launch();
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// sensitivity mode: J[t][p] = sum of the far-field values of t's pieces (piece order) + the
+// near-field results of t's deferred pieces (piece order) -- the same summation structure as a
+// forward run of the one-tesseroid model [t].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+jac_reduce(int64_t n_tess, int64_t n_points, const int64_t *__restrict__ tess_offset,
+           const double *__restrict__ jq, int64_t n_pairs,
+           const unsigned long long *__restrict__ keys, const double *__restrict__ pair_result,
+           double *__restrict__ out)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_points)
+        return;
+    for (int64_t t = blockIdx.y; t < n_tess; t += gridDim.y) {
+    const int64_t q0 = tess_offset[t], q1 = tess_offset[t + 1];
+    double far = 0.0;
+    bool any_near = false;
+    for (int64_t q = q0; q < q1; q++) {
+        const double v = jq[q * n_points + p];
+        if (v != v)
+            any_near = true;
+        else
+            far += v;
+    }
+    double r = far;
+    if (any_near && n_pairs > 0) {
+        double near = 0.0;
+        for (int64_t q = q0; q < q1; q++) {
+            const double v = jq[q * n_points + p];
+            if (v == v)
+                continue;
+            const unsigned long long key = ((unsigned long long)p << 32) | (unsigned long long)q;
+            int64_t lo = 0, hi = n_pairs;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (keys[mid] < key)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            // a pair that is not in the queue produced a genuine NaN in the sweep
+            near += (lo < n_pairs && keys[lo] == key) ? pair_result[lo] : v;
+        }
+        r += near;
+    }
+    out[t * n_points + p] = r;
+    }
+}
+
+cudaError_t tvd_launch_jac_reduce(const PieceTable &t, int64_t n_points, const double *jac_pieces,
+                                  int64_t n_pairs, const unsigned long long *keys,
+                                  const double *pair_result, double *jac_out, cudaStream_t stream)
+{
+    if (n_points == 0 || t.n_tess == 0)
+        return cudaSuccess;
+    dim3 grid((unsigned)((n_points + 255) / 256), (unsigned)(t.n_tess < 65535 ? t.n_tess : 65535));
+    jac_reduce<<<grid, 256, 0, stream>>>(t.n_tess, n_points, t.tess_offset, jac_pieces, n_pairs,
+                                         keys, pair_result, jac_out);
+    tvd_count_launch();
+    return cudaGetLastError();
+}

@@ -260,6 +260,43 @@ def fields(names, lon, lat, height, model, dens=None, ratios=None, njobs=1, pool
     return {f: (raw[f] * _UNITS[f]).reshape(shape) for f in names}
 
 
+def sensitivity(field, lon, lat, height, model, dens=None, ratio=None, delta=DELTA, device=0):
+    """
+    Sensitivity (Jacobian) matrix ``A`` of shape ``(n_points, n_tesseroids)``:
+    ``A[p, t]`` = `field` at point ``p`` due to tesseroid ``t`` alone, so that
+    ``A.sum(axis=1)`` is the forward-modelled field.  With ``dens=1`` this is the classic
+    density sensitivity the reference's docstring mentions for the ``dens`` argument
+    (tesseroid.py:347-349), which the reference builds one single-tesseroid call per column;
+    column ``t`` here is bit-identical to that call.  Tesseroids the reference would skip
+    (``None``, no density) get no column: columns follow the flattened model.
+    """
+    lib = _lib.load()
+    if ratio is None:
+        ratio = _DEFAULT_RATIO[field]
+    lon, lat, height = np.asarray(lon), np.asarray(lat), np.asarray(height)
+    _check_input(lon, lat, height, model, ratio, 1, None)
+    cc = [_lib.as_f64(a) for a in _convert_coords(
+        np.asarray(lon, dtype=np.float64).ravel(), np.asarray(lat, dtype=np.float64).ravel(),
+        np.asarray(height, dtype=np.float64).ravel())]
+    own = not isinstance(model, PreparedModel)
+    prepared = PreparedModel(model, dens=dens, delta=delta, device=device) if own else model
+    try:
+        n, nt = cc[0].size, prepared.n_tesseroids
+        jac = np.zeros((nt, n))
+        stats = np.zeros(_lib.NSTATS, dtype=np.int64)
+        rc = lib.tvd_sensitivity(_lib.FIELDS[field], prepared.handle, n, *[_lib.ptr_f64(a) for a in cc],
+                                 float(ratio), int(STACK_SIZE), int(device), _lib.ptr_f64(jac),
+                                 _lib.ptr_i64(stats))
+        _lib.check(rc, "tvd_sensitivity")
+    finally:
+        if own:
+            prepared.close()
+    if stats[3] != 0:
+        warnings.warn(_WARNING_MSG, RuntimeWarning)
+    jac *= _UNITS[field]
+    return jac.T
+
+
 def _dispatcher(field, lon, lat, height, model, **kwargs):
     """Counterpart of the reference's ``_dispatcher`` + ``_forward_model``
     (tesseroid.py:164-234): one preprocessing call and one batched forward call."""
