@@ -145,8 +145,9 @@ int tvd_forward(int field, tvd_model *model, int64_t n_points, const double *lon
 /*
  * Several fields of the same model on the same points in ONE far-field sweep:
  * the fields share the far test, the angular half of the quadrature, l^2 and its inverse square
- * root; each field keeps its own distance-size ratio, near-field queue and literal walk, and its
- * values are bit-identical to a separate tvd_forward call.  The reference needs one full pass
+ * root; each field keeps its own distance-size ratio, near-field queue and literal walk; its
+ * subdivision counts are those of a separate tvd_forward call and its values agree with it to a
+ * few ulp (bit-identical for {gx, gy, gz} and for the six tensor components).  The reference needs one full pass
  * per field (tesseroid.py:377,435,493,556).
  *
  *   n_fields, fields, ratios   distinct tvd_field ids and the ratio D of each

@@ -74,6 +74,20 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     return fma(y0, q, y0);
 }
 
+// x^(-3/2) directly from the same seed (one operation fewer than cubing rsqrt_fast):
+//   e = 1 - x*y0^2 ;  x^(-3/2) = y0^3 (1 - e)^(-3/2) = y0^3 (1 + 3e/2 + 15e^2/8 + O(e^3))
+__device__ __forceinline__ double rsqrt3_fast(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double s = y0 * y0;
+    const double e = fma(-x, s, 1.0);
+    const double c = s * y0;
+    const double p = fma(1.875, e, 1.5);
+    const double q = e * p;
+    return fma(c, q, c);
+}
+
 // ---------------------------------------------------------------------------------------------
 // cos / sincos of the longitude difference.
 //
@@ -136,8 +150,8 @@ __device__ __forceinline__ void trig2(double x0, double x1, double &c0, double &
 // ---------------------------------------------------------------------------------------------
 // The sweep is compiled for a MASK of fields (bit f = tvd_field f).  A single field is the
 // one-bit mask; fused sets (e.g. potential + gz + gzz) share the far test, the angular half, l^2
-// and its inverse square root between their fields.  Per field the arithmetic is the same in
-// every mask, so a field's far-field sum does not depend on which other fields ride along.
+// and its inverse square root between their fields (a field's values then agree with its
+// single-field sweep to a few ulp: l^-3 is refined directly when only gx/gy/gz are asked for).
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int mask_count(int m)
 {
@@ -260,13 +274,17 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const double l_sqr = b[k] - a[k] * cospsi;
-                const double y = rsqrt_fast(l_sqr);
                 const double w = wjk[j][k];
-                double y3 = 0.0, y5 = 0.0, dx = 0.0, dy = 0.0, dz = 0.0;
-                if (T::needs_y3)
-                    y3 = y * y * y;
-                if (T::needs_y5)
-                    y5 = y3 * y * y;
+                double y = 0.0, y3 = 0.0, y5 = 0.0, dx = 0.0, dy = 0.0, dz = 0.0;
+                if (T::needs_y5 || mask_has(MASK, TVD_POTENTIAL)) {
+                    y = rsqrt_fast(l_sqr);
+                    if (T::needs_y3)
+                        y3 = y * y * y;
+                    if (T::needs_y5)
+                        y5 = y3 * y * y;
+                } else {
+                    y3 = rsqrt3_fast(l_sqr);       // gx, gy, gz only need l^-3
+                }
                 // rc*cospsi - radius (:487); the product is not ill-conditioned enough to need
                 // the reference's separate rounding (<= 5e-14 relative)
                 if (T::needs_dz)

@@ -183,7 +183,7 @@ def forward_raw_fused(fields, lon_rad, sinlat, coslat, radius, prepared, ratios,
                       devices=None, return_stats=False):
     """
     Several fields in one far-field sweep (``tvd_forward_fused``): ``{field: array}`` in kernel
-    units; each field's values are bit-identical to a separate :func:`forward_raw` call.
+    units; each field's values agree with a separate :func:`forward_raw` call to a few ulp.
     """
     lib = _lib.load()
     lon_rad, sinlat = _lib.as_f64(lon_rad), _lib.as_f64(sinlat)
@@ -232,7 +232,7 @@ def fields(names, lon, lat, height, model, dens=None, ratios=None, njobs=1, pool
     The reference computes one field per call, each a full pass over points x tesseroids
     (tesseroid.py:377,435,493,556).  Here the model is flattened and discretised once, and field
     sets the far-field sweep is compiled for (see ``include/tvd.h``) share one sweep; other sets
-    run field by field.  Values are bit-identical to the single-field functions; ``ratios``
+    run field by field.  Values agree with the single-field functions to a few ulp; ``ratios``
     defaults to each field's own default (1 / 2.5 / 8).
     """
     names = list(names)

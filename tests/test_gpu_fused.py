@@ -1,4 +1,8 @@
-"""Fused multi-field sweeps: same bits as the single-field calls."""
+"""
+Fused multi-field sweeps against the single-field calls: identical counters, and
+values equal to a few ulp (bit-identical when the set uses the same l^-3 evaluation as the single
+fields: {gx, gy, gz} and the six tensor components).
+"""
 import numpy as np
 import pytest
 
@@ -30,7 +34,12 @@ def test_fused_equals_single_field_calls(names, grid):
     fused, fstats = forward_raw_fused(names, *cc, pm, ratios, return_stats=True)
     for f, r in zip(names, ratios):
         single, sstats = forward_raw(f, *cc, pm, r, return_stats=True)
-        assert np.array_equal(fused[f], single), f
+        if set(names) <= {"gx", "gy", "gz"} or set(names) <= set(cases.ALL_FIELDS[4:]):
+            assert np.array_equal(fused[f], single), f
+        else:
+            scale = max(np.max(np.abs(forward_raw(g, *cc, pm, cases.DEFAULT_RATIO[g])))
+                        for g in names if cases.UNIT[g] == cases.UNIT[f])
+            assert np.max(np.abs(fused[f] - single)) <= 1e-14 * scale, f
         assert fstats[f] == sstats, f
     pm.close()
 
@@ -57,9 +66,9 @@ def test_fields_api():
     mesh, _, exact = cases.exponential_case(1e4, 10)
     lats, lons, heights = cases.GRIDS["260km"]()
     out = tesseroid.fields(["potential", "gz", "gzz"], lons, lats, heights, mesh, delta=0.1)
-    assert np.array_equal(out["gz"], tesseroid.gz(lons, lats, heights, mesh, delta=0.1))
-    assert np.array_equal(out["gzz"], tesseroid.gzz(lons, lats, heights, mesh, delta=0.1))
-    assert np.array_equal(out["potential"], tesseroid.potential(lons, lats, heights, mesh, delta=0.1))
+    for f in ("potential", "gz", "gzz"):
+        single = getattr(tesseroid, f)(lons, lats, heights, mesh, delta=0.1)
+        assert np.max(np.abs(out[f] - single)) <= 1e-14 * np.max(np.abs(single))
     ex = exact(heights[0])
     for f in out:
         assert cases.percent_difference(out[f], ex[f]) <= 0.1
