@@ -104,7 +104,10 @@ template <bool WANT_SIN>
 __device__ __forceinline__ void trig2(double x0, double x1, double &c0, double &c1, double &s0,
                                       double &s1)
 {
-    const bool small = fmax(fabs(x0), fabs(x1)) <= TVD_PIO4;
+    // |x| < pi/4 decided on the high words with integer compares (the FP64 pipe is the scarce
+    // resource): hi(|x|) < hi(pi/4) = 0x3fe921fb; NaN and inf fail the test
+    const bool small = ((__double2hiint(x0) & 0x7fffffff) < 0x3fe921fb) &&
+                       ((__double2hiint(x1) & 0x7fffffff) < 0x3fe921fb);
     if (__all_sync(0xffffffffu, small)) {
         c0 = kcos0(x0);
         c1 = kcos0(x1);
