@@ -191,15 +191,21 @@ def cpu_sample_run(n_tess, n_points, n_threads, seed=1):
     return n_tess * n_points / dt, dt, kind
 
 
+def _size_sample(rate, seconds, cores):
+    pairs = max(3600.0, rate * seconds)
+    n_t = max(60, min(int(np.sqrt(pairs)), 4000))
+    n_p = max(cores, min(int(pairs / n_t), 100000))
+    return n_t, n_p
+
+
 def cpu_baseline(target_s=12.0):
     """Bounded CPU sample (about 10-30 s of CPU work in total), all host cores."""
     cores = os.cpu_count() or 1
-    # calibrate on a tiny sample, then size the real one
+    # calibrate on a tiny sample (dominated by the pool start-up), then on a 2 s one
     rate, dt, kind = cpu_sample_run(60, 60 * max(1, cores // 8), cores)
-    pairs = max(3600.0, rate * target_s)
-    n = int(np.sqrt(pairs))
-    n_t = max(60, min(n, 4000))
-    n_p = max(cores, min(int(pairs / n_t), 100000))
+    n_t, n_p = _size_sample(rate, 2.0, cores)
+    rate, dt, kind = cpu_sample_run(n_t, n_p, cores)
+    n_t, n_p = _size_sample(rate, target_s, cores)
     rate, dt, kind = cpu_sample_run(n_t, n_p, cores)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": "%d random tesseroids x %d random grid points of the C4 workload, "
@@ -212,10 +218,9 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     rate, dt, kind = cpu_sample_run(60, 60 * max(1, cores // 8), cores)      # calibration
-    per_step_s = 8.0
-    pairs = max(3600.0, rate * per_step_s)
-    n_t = max(60, min(int(np.sqrt(pairs)), 4000))
-    n_p = max(cores, min(int(pairs / n_t), 100000))
+    n_t, n_p = _size_sample(rate, 2.0, cores)
+    rate, dt, kind = cpu_sample_run(n_t, n_p, cores)
+    n_t, n_p = _size_sample(rate, 8.0, cores)                                # ~8 s per step
     for w in range(args.warmup):
         cpu_sample_run(n_t, max(cores, n_p // 8), cores, seed=100 + w)
     t_total, evals = 0.0, 0
@@ -374,7 +379,10 @@ def run_gpu(args):
             "piece_pairs_per_s": float(n_pieces) * P * args.steps * world / (ms * 1e-3),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if (achieved and peak > 0) else None,
-                         "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this
+                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r1d.md);
+                         # the algorithmic minimum is the piece records read once, 281 MB
+                         "traffic": 312.1e6 if P == 75776 else None,
                          "kernel": "far_sweep<gz>",
                          "kernel_ms_per_launch": far_ms / max(1, nfar.value),
                          "kernel_share_of_step": far_ms / ms,

@@ -423,27 +423,39 @@ far_sweep(const FarArgs a)
         int nq = (int)((q_end - q0) < TVD_TILE ? (q_end - q0) : TVD_TILE);
         const double *tt = s_test[st];
         const double *gg = s_glq[st];
+        // d^2-part of the far test of piece qi, computed one piece ahead so that its dependent
+        // FMA chain overlaps the radial work of the previous piece
+        // conservative far-field test: d^2 - thr_f^2 = r^2 + (rt^2 - thr_f^2) - 2 p.c > 0 with
+        // p, c the Cartesian position vectors of the point and the piece centre
+        // (FMA allowed: only the guarded comparison depends on it, see K4)
+        auto far_value = [&](int qi) -> double {
+            const double *trec = tt + qi * TREC;
+            if (NF == 1) {
+                const double2 cxy = *reinterpret_cast<const double2 *>(trec + 0);
+                const double2 czk = *reinterpret_cast<const double2 *>(trec + 2);
+                double t = fma(pt.p2x, cxy.x, czk.y);
+                t = fma(pt.p2y, cxy.y, t);
+                return fma(pt.p2z, czk.x, t);
+            } else {
+                double t = pt.p2x * trec[0];
+                t = fma(pt.p2y, trec[1], t);
+                return fma(pt.p2z, trec[2], t);
+            }
+        };
+        double t_next = nq > 0 ? far_value(0) : 0.0;
         for (int qi = 0; qi < nq; qi++) {
             const double *trec = tt + qi * TREC;
             const double *grec = gg + qi * TVD_GLQ_REC;
             // record flag: this piece has the lon/lat extent of the previous piece of the tile
             // (a further radial piece of the same tesseroid) -> keep the angular half
             const bool same_extent = reinterpret_cast<const int2 *>(grec + 14)->x != 0;
-            // conservative far-field test: d^2 - thr_f^2 = r^2 + (rt^2 - thr_f^2) - 2 p.c > 0 with
-            // p, c the Cartesian position vectors of the point and the piece centre
-            // (FMA allowed: only the guarded comparison depends on it, see K4)
+            const double t = t_next;
+            if (qi + 1 < nq)
+                t_next = far_value(qi + 1);
             bool far[NF];
             if (NF == 1) {
-                const double2 cxy = *reinterpret_cast<const double2 *>(trec + 0);
-                const double2 czk = *reinterpret_cast<const double2 *>(trec + 2);
-                double t = fma(pt.p2x, cxy.x, czk.y);
-                t = fma(pt.p2y, cxy.y, t);
-                t = fma(pt.p2z, czk.x, t);
                 far[0] = t > pt.neg_r_sqr;
             } else {
-                double t = pt.p2x * trec[0];
-                t = fma(pt.p2y, trec[1], t);
-                t = fma(pt.p2z, trec[2], t);
 #pragma unroll
                 for (int s = 0; s < NF; s++)
                     far[s] = (t + trec[3 + s]) > pt.neg_r_sqr;
