@@ -16,9 +16,9 @@
 #include "tvd_internal.cuh"
 
 // Near-field pairs are the worst-conditioned ones (cos psi and l^2 cancel hardest for the closest
-// cells), and there are few of them: all trigonometry of the literal walk is evaluated in
-// double-double and rounded once (tvd_ddmath.cuh), i.e. it equals glibc's result wherever glibc
-// rounds correctly.
+// cells), and there are few of them: the trigonometry of the integration nodes (scale_nodes and
+// cos(lon - lonc)) is evaluated in double-double and rounded once (tvd_ddmath.cuh), i.e. it
+// equals glibc's result wherever glibc rounds correctly.
 
 struct Level {
     double w, s, dlon, dlat;
@@ -144,15 +144,17 @@ near_walk(const NearArgs a)
     stktop -= 1;                                          // pop of the root (:81)
     while (true) {
         nodes++;
-        // distance_n_size (:104-123)
+        // distance_n_size (:104-123).  These values only feed the split decision, where a last-bit
+        // difference matters only within ~1e-9 of the threshold: the fast sin/cos are used here,
+        // the double-double ones are kept for the integration nodes below.
         const double lont = TVD_D2R * 0.5 * (w + e);
         const double latt = TVD_D2R * 0.5 * (s + n);
-        const double sinlatt = dd_sin(latt), coslatt = dd_cos(latt);
-        const double cospsi = sinlat * sinlatt + coslat * coslatt * dd_cos(lon - lont);
+        const double sinlatt = tvd_sin(latt), coslatt = tvd_cos(latt);
+        const double cospsi = sinlat * sinlatt + coslat * coslatt * tvd_cos(lon - lont);
         const double distance = sqrt(radius * radius + rt * rt - 2 * radius * rt * cospsi);
-        const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * dd_cos(TVD_D2R * (e - w)));
-        const double Llat = rtop * acos(dd_sin(TVD_D2R * n) * dd_sin(TVD_D2R * s) +
-                                        dd_cos(TVD_D2R * n) * dd_cos(TVD_D2R * s));
+        const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * tvd_cos(TVD_D2R * (e - w)));
+        const double Llat = rtop * acos(tvd_sin(TVD_D2R * n) * tvd_sin(TVD_D2R * s) +
+                                        tvd_cos(TVD_D2R * n) * tvd_cos(TVD_D2R * s));
         // divisions (:129-146)
         int nlon = 1, nlat = 1;
         if (distance <= a.ratio * Llon) {
