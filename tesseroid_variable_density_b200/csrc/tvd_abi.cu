@@ -471,9 +471,9 @@ extern "C" int tvd_model_get_pieces(const tvd_model *m, double *top, double *bot
 // ---------------------------------------------------------------------------------------------
 static int plan_groups(int64_t n_pieces, int64_t n_points_total)
 {
-    // Enough thread blocks for ~2 waves of 4 resident 128-thread blocks on 148 SMs, but never
-    // groups smaller than 4 tiles.  Pure function of (Q, P_total).
-    const int64_t ppb = (int64_t)TVD_FAR_THREADS * TVD_FAR_PPT;
+    // Enough thread blocks for ~2 waves on 148 SMs, but never groups smaller than 4 tiles.
+    // Pure function of (Q, P_total).
+    const int64_t ppb = (int64_t)TVD_FAR_THREADS;
     const int64_t blocks_x = (n_points_total + ppb - 1) / ppb;
     if (blocks_x <= 0 || n_pieces <= 0)
         return 1;

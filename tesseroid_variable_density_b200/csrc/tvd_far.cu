@@ -570,10 +570,16 @@ __global__ void __launch_bounds__(256) dfma_probe(double *out, int iters, double
 #pragma unroll
     for (int i = 0; i < 16; i++)
         acc[i] = (double)(threadIdx.x + i);
-    for (int it = 0; it < iters; it++) {
+    // 16 independent chains, 16 x 16 = 256 DFMA per loop iteration: an FP64 warp instruction
+    // occupies the issue port for two cycles and nothing else issues in its shadow, so the loop
+    // overhead (3 instructions) must be negligible for the probe to see the pipe's peak
+    for (int it = 0; it < iters; it += 16) {
 #pragma unroll
-        for (int i = 0; i < 16; i++)
-            acc[i] = fma(acc[i], x, y);
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                acc[i] = fma(acc[i], x, y);
+        }
     }
     double s = 0;
 #pragma unroll
@@ -604,7 +610,7 @@ double tvd_fp64_probe(int iters, cudaStream_t stream)
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+        const double flops = 2.0 * 16.0 * (double)((iters + 15) / 16 * 16) * (double)blocks * threads;
         const double tf = flops / (ms * 1e-3) / 1e12;
         if (tf > best)
             best = tf;

@@ -26,12 +26,9 @@ __host__ __device__ constexpr int tvd_test_rec_len(int nf) { return ((3 + nf) + 
 #define TVD_MASK_TENSOR ((1 << TVD_GXX) | (1 << TVD_GXY) | (1 << TVD_GXZ) | (1 << TVD_GYY) | \
                          (1 << TVD_GYZ) | (1 << TVD_GZZ))
 #define TVD_TILE 64                         // pieces per shared-memory tile
-// far-field sweep launch shape: threads per block, points per thread, resident blocks per SM
+// far-field sweep launch shape: threads (= points) per block, resident blocks per SM
 #ifndef TVD_FAR_THREADS
 #define TVD_FAR_THREADS 512
-#endif
-#ifndef TVD_FAR_PPT
-#define TVD_FAR_PPT 1
 #endif
 #ifndef TVD_FAR_MINBLOCKS
 #define TVD_FAR_MINBLOCKS 1
