@@ -102,6 +102,7 @@ static void free_table(PieceTable &t)
     cudaFree(t.tess_params);
     cudaFree(t.tess_npieces);
     cudaFree(t.tess_offset);
+    cudaFree(t.sweep_piece);
     cudaFree(t.top);
     cudaFree(t.bottom);
     cudaFree(t.parent);
@@ -534,6 +535,7 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
 
     // K4: GLQ records once per model, test records per (field set, ratios)
     if (!c->glq_packed) {
+        CUDA_TRY(tvd_build_sweep_order(c->tab, stream));
         CUDA_TRY(c->glq_rec.reserve((size_t)Q * TVD_GLQ_REC * sizeof(double)));
         CUDA_TRY(c->geom.reserve((size_t)Q * 5 * sizeof(double)));
         CUDA_TRY(tvd_launch_pack_glq(c->tab, c->glq_rec.as<double>(), c->geom.as<double>(), stream));

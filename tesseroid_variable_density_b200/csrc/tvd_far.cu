@@ -195,31 +195,39 @@ struct PointRegs {
 };
 
 // The angular half of the root GLQ: everything that depends on the piece only through its
-// lon/lat extent.  The radial pieces of one tesseroid share it, so it is recomputed only when
-// the record says the extent changed.
+// lon/lat extent.  The sweep visits the pieces sorted by longitude extent, so
+//   - the longitude part (cos/sin of lon - lonc_i) is recomputed only when the extent in
+//     longitude changes (once per column of a regular mesh),
+//   - the latitude part (cos psi_ij, k_phi_ij) once per tesseroid,
+//   - the radial pieces of one tesseroid share both.
 struct Angular {
+    double coslon[2];
+    double sinlon[2];
     double cospsi[2][2];     // [i][j]
     double kphi[2][2];
-    double sinlon[2];
     double clc[2];           // coslatc[j]
 };
 
 template <int MASK>
-__device__ __forceinline__ void glq_angular(const PointRegs &pt, const double *__restrict__ g,
-                                            Angular &A)
+__device__ __forceinline__ void glq_lon(const PointRegs &pt, const double *__restrict__ g,
+                                        Angular &A)
 {
     typedef MaskTraits<MASK> T;
     const double2 lonc = *reinterpret_cast<const double2 *>(g + 0);
+    // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
+    double s0 = 0.0, s1 = 0.0;
+    trig2<T::needs_sinlon>(pt.lon - lonc.x, pt.lon - lonc.y, A.coslon[0], A.coslon[1], s0, s1);
+    A.sinlon[0] = -s0;
+    A.sinlon[1] = -s1;
+}
+
+template <int MASK>
+__device__ __forceinline__ void glq_lat(const PointRegs &pt, const double *__restrict__ g,
+                                        Angular &A)
+{
+    typedef MaskTraits<MASK> T;
     const double2 sinlatc = *reinterpret_cast<const double2 *>(g + 2);
     const double2 coslatc = *reinterpret_cast<const double2 *>(g + 4);
-    double coslon[2];
-    {
-        // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
-        double s0 = 0.0, s1 = 0.0;
-        trig2<T::needs_sinlon>(pt.lon - lonc.x, pt.lon - lonc.y, coslon[0], coslon[1], s0, s1);
-        A.sinlon[0] = -s0;
-        A.sinlon[1] = -s1;
-    }
     // reference order: sinlat*sinlatc[j] + coslat*coslatc[j]*coslon   (:244), no contraction
     const double ss[2] = {pt.sinlat * sinlatc.x, pt.sinlat * sinlatc.y};
     const double cc[2] = {pt.coslat * coslatc.x, pt.coslat * coslatc.y};
@@ -230,9 +238,9 @@ __device__ __forceinline__ void glq_angular(const PointRegs &pt, const double *_
     for (int i = 0; i < 2; i++) {
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            A.cospsi[i][j] = ss[j] + cc[j] * coslon[i];
+            A.cospsi[i][j] = ss[j] + cc[j] * A.coslon[i];
             if (T::needs_kphi)
-                A.kphi[i][j] = pt.coslat * slc[j] - pt.sinlat * A.clc[j] * coslon[i];   // :322
+                A.kphi[i][j] = pt.coslat * slc[j] - pt.sinlat * A.clc[j] * A.coslon[i];   // :322
         }
     }
 }
@@ -446,9 +454,11 @@ far_sweep(const FarArgs a)
         for (int qi = 0; qi < nq; qi++) {
             const double *trec = tt + qi * TREC;
             const double *grec = gg + qi * TVD_GLQ_REC;
-            // record flag: this piece has the lon/lat extent of the previous piece of the tile
-            // (a further radial piece of the same tesseroid) -> keep the angular half
-            const bool same_extent = reinterpret_cast<const int2 *>(grec + 14)->x != 0;
+            // record flags (previous piece of the same tile): bit 0 = same tesseroid (a further
+            // radial piece) -> keep the whole angular half; bit 1 = same extent in longitude ->
+            // keep its longitude part.  Slot 15 = the piece's index in the model-order table.
+            const int flags = reinterpret_cast<const int2 *>(grec + 14)->x;
+            const long long q_model = reinterpret_cast<const long long *>(grec)[15];
             const double t = t_next;
             if (qi + 1 < nq)
                 t_next = far_value(qi + 1);
@@ -474,20 +484,22 @@ far_sweep(const FarArgs a)
                         const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
                         if (idx < a.qcap)
                             a.queue[(unsigned long long)s * a.qcap + idx] =
-                                ((unsigned long long)pidx << 32) | (unsigned long long)(q0 + qi);
+                                ((unsigned long long)pidx << 32) | (unsigned long long)q_model;
                     }
                 }
             }
             // every lane evaluates the root GLQ (it contains warp-wide votes); lanes whose pair
             // was deferred simply drop the value
-            if (!same_extent)
-                glq_angular<MASK>(pt, grec, ang);
+            if (!(flags & 2))
+                glq_lon<MASK>(pt, grec, ang);
+            if (!(flags & 1))
+                glq_lat<MASK>(pt, grec, ang);
             double v[NF];
             glq_radial<MASK>(pt, grec, ang, v);
             if (JAC) {
                 // sensitivity mode: one value per (piece, point); NaN marks a deferred pair
                 if (valid)
-                    a.jac[(q0 + qi) * a.n_points + pidx] =
+                    a.jac[q_model * a.n_points + pidx] =
                         far[0] ? v[0] : __longlong_as_double(0x7ff8000000000000ll);
             } else {
 #pragma unroll

@@ -184,6 +184,8 @@ struct PieceTable {
     double *tess_params = nullptr;   // [n_tess][TVD_NPAR]
     int32_t *tess_npieces = nullptr; // [n_tess]
     int64_t *tess_offset = nullptr;  // [n_tess + 1] first piece of each tesseroid
+    int32_t *sweep_piece = nullptr;  // [n_pieces] sweep position -> piece (pieces sorted by the
+                                     // longitude extent of their tesseroid, see tvd_build_sweep_order)
     double *top = nullptr;           // [n_pieces]
     double *bottom = nullptr;        // [n_pieces]
     int32_t *parent = nullptr;       // [n_pieces]
@@ -229,6 +231,12 @@ cudaError_t tvd_launch_far(const FarArgs &a, cudaStream_t stream);
 cudaError_t tvd_launch_jac_reduce(const PieceTable &t, int64_t n_points, const double *jac_pieces,
                                   int64_t n_pairs, const unsigned long long *keys,
                                   const double *pair_result, double *jac_out, cudaStream_t stream);
+// Order in which the far-field sweep visits the pieces: tesseroids stably sorted by their
+// longitude extent (w, e), each followed by its radial pieces.  Fills t.sweep_piece.
+cudaError_t tvd_build_sweep_order(PieceTable &t, cudaStream_t stream);
+cudaError_t tvd_sort_pairs(void *d_temp, size_t &temp_bytes, const unsigned long long *keys_in,
+                           unsigned long long *keys_out, const int32_t *vals_in,
+                           int32_t *vals_out, int64_t n, cudaStream_t stream);
 // sort of the near-field pair keys (CUB radix sort; bookkeeping, tvd_sort.cu)
 cudaError_t tvd_sort_keys(void *d_temp, size_t &temp_bytes, const unsigned long long *in,
                           unsigned long long *out, int64_t n, int end_bit, cudaStream_t stream);

@@ -243,11 +243,107 @@ cudaError_t tvd_launch_scan(const int32_t *d_counts, int64_t *d_offsets, int64_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// sweep order: tesseroids stably sorted by the bit patterns of (w, e); any total order works,
+// the point is that tesseroids with the same extent in longitude (a column of a regular mesh)
+// become neighbours, so the sweep computes cos(lon - lonc) once per column
+// ---------------------------------------------------------------------------------------------
+__global__ void sweep_keys(int64_t n, const double *__restrict__ bounds, int which,
+                           const int32_t *__restrict__ idx_in, unsigned long long *__restrict__ keys,
+                           int32_t *__restrict__ idx_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const int64_t t = idx_in ? idx_in[i] : i;
+    keys[i] = (unsigned long long)__double_as_longlong(bounds[6 * t + which]);
+    if (idx_out)
+        idx_out[i] = (int32_t)t;
+}
+__global__ void sweep_counts(int64_t n, const int32_t *__restrict__ order,
+                             const int32_t *__restrict__ npieces, int32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = npieces[order[i]];
+}
+__global__ void sweep_expand(int64_t n, const int32_t *__restrict__ order,
+                             const int64_t *__restrict__ tess_offset,
+                             const int64_t *__restrict__ sweep_offset,
+                             int32_t *__restrict__ sweep_piece)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const int64_t t = order[i];
+    const int64_t q0 = tess_offset[t], np = tess_offset[t + 1] - q0, o = sweep_offset[i];
+    for (int64_t k = 0; k < np; k++)
+        sweep_piece[o + k] = (int32_t)(q0 + k);
+}
+
+cudaError_t tvd_build_sweep_order(PieceTable &t, cudaStream_t stream)
+{
+    if (t.sweep_piece != nullptr || t.n_pieces == 0)
+        return cudaSuccess;
+    const int64_t n = t.n_tess;
+    unsigned long long *key_a = nullptr, *key_b = nullptr;
+    int32_t *idx_a = nullptr, *idx_b = nullptr, *cnt = nullptr;
+    int64_t *off = nullptr;
+    void *temp = nullptr;
+    size_t temp_bytes = 0;
+    cudaError_t e = cudaMalloc(&t.sweep_piece, (size_t)t.n_pieces * sizeof(int32_t));
+    auto done = [&](cudaError_t err) {
+        cudaFree(key_a);
+        cudaFree(key_b);
+        cudaFree(idx_a);
+        cudaFree(idx_b);
+        cudaFree(cnt);
+        cudaFree(off);
+        cudaFree(temp);
+        if (err != cudaSuccess) {
+            cudaFree(t.sweep_piece);
+            t.sweep_piece = nullptr;
+        }
+        return err;
+    };
+    if (e != cudaSuccess)
+        return done(e);
+#define SW_TRY(x)              \
+    do {                       \
+        e = (x);               \
+        if (e != cudaSuccess)  \
+            return done(e);    \
+    } while (0)
+    SW_TRY(cudaMalloc(&key_a, n * sizeof(unsigned long long)));
+    SW_TRY(cudaMalloc(&key_b, n * sizeof(unsigned long long)));
+    SW_TRY(cudaMalloc(&idx_a, n * sizeof(int32_t)));
+    SW_TRY(cudaMalloc(&idx_b, n * sizeof(int32_t)));
+    SW_TRY(cudaMalloc(&cnt, n * sizeof(int32_t)));
+    SW_TRY(cudaMalloc(&off, (n + 1) * sizeof(int64_t)));
+    SW_TRY(tvd_sort_pairs(nullptr, temp_bytes, key_a, key_b, idx_a, idx_b, n, stream));
+    SW_TRY(cudaMalloc(&temp, temp_bytes ? temp_bytes : 16));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    // LSD: first by e, then (stably) by w
+    sweep_keys<<<blocks, 256, 0, stream>>>(n, t.tess_bounds, 1, nullptr, key_a, idx_a);
+    SW_TRY(tvd_sort_pairs(temp, temp_bytes, key_a, key_b, idx_a, idx_b, n, stream));
+    sweep_keys<<<blocks, 256, 0, stream>>>(n, t.tess_bounds, 0, idx_b, key_a, nullptr);
+    SW_TRY(tvd_sort_pairs(temp, temp_bytes, key_a, key_b, idx_b, idx_a, n, stream));
+    sweep_counts<<<blocks, 256, 0, stream>>>(n, idx_a, t.tess_npieces, cnt);
+    SW_TRY(tvd_launch_scan(cnt, off, n, stream));
+    sweep_expand<<<blocks, 256, 0, stream>>>(n, idx_a, t.tess_offset, off, t.sweep_piece);
+    tvd_count_launch(4);
+    SW_TRY(cudaGetLastError());
+    SW_TRY(cudaStreamSynchronize(stream));
+#undef SW_TRY
+    return done(cudaSuccess);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4: root records
 // ---------------------------------------------------------------------------------------------
+// Records are stored in SWEEP order (PieceTable::sweep_piece).
 // glq record  [16]: lonc0 lonc1 sinlatc0 sinlatc1 coslatc0 coslatc1 rc0 rc1 rc0^2 rc1^2
 //                   w00 w01 w10 w11 (w[j][k] = rho_k * kappa_jk * scale)
-//                   same-extent flag (int64)  (pad)
+//                   flags (int64)  model-order piece index (int64)
 // geometry     [5]: cx cy cz (Cartesian centre of the piece)  rt^2  max(Llon, Llat)
 // test record: cx cy cz K_0 .. K_{nf-1} with K_f = rt^2 - thr2(ratio_f); thr2 is the conservative
 //   far-field threshold on the squared centre distance, see tvd_far.cu; pairs that do not clear
@@ -257,12 +353,14 @@ __global__ void __launch_bounds__(128)
 k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
             const int32_t *__restrict__ tess_kind, const double *__restrict__ tess_params,
             const double *__restrict__ ptop, const double *__restrict__ pbottom,
-            const int32_t *__restrict__ parent, double *__restrict__ glq_rec,
-            double *__restrict__ geom)
+            const int32_t *__restrict__ parent, const int32_t *__restrict__ sweep_piece,
+            double *__restrict__ glq_rec, double *__restrict__ geom)
 {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_pieces)
+    // one thread per sweep position qs; q = the piece (model order) visited there
+    const int64_t qs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qs >= n_pieces)
         return;
+    const int64_t q = sweep_piece[qs];
     const int64_t t = parent[q];
     const double w = tess_bounds[6 * t + 0], e = tess_bounds[6 * t + 1];
     const double s = tess_bounds[6 * t + 2], n = tess_bounds[6 * t + 3];
@@ -282,7 +380,7 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
     const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * dd_cos(TVD_D2R * (e - w)));
     const double Llat = rtop * acos(dd_sin(TVD_D2R * n) * dd_sin(TVD_D2R * s) +
                                     dd_cos(TVD_D2R * n) * dd_cos(TVD_D2R * s));
-    double *gm = geom + TVD_GEOM_REC * q;
+    double *gm = geom + TVD_GEOM_REC * qs;
     gm[0] = rt * (coslatt * dd_cos(lont));     // centre of the piece, geocentric Cartesian
     gm[1] = rt * (coslatt * dd_sin(lont));
     gm[2] = rt * sinlatt;
@@ -306,7 +404,7 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
         dens[i] = tvd_density_cr(kind, p, rc[i] - TVD_R);   // :274 (or the constant, :250)
     }
     const double scale = TVD_D2R * dlon * TVD_D2R * dlat * dr * 0.125;
-    double *g = glq_rec + TVD_GLQ_REC * q;
+    double *g = glq_rec + TVD_GLQ_REC * qs;
     g[0] = lonc[0];
     g[1] = lonc[1];
     g[2] = sinlatc[0];
@@ -325,11 +423,20 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
             g[10 + 2 * j + k] = dens[k] * kappa * scale;
         }
     }
-    // flag (as a 64-bit integer): same lon/lat extent as the previous piece of the same tile,
-    // i.e. a further radial piece of the same tesseroid -> the sweep keeps its angular half
-    const bool same = (q % TVD_TILE) != 0 && parent[q - 1] == parent[q];
-    reinterpret_cast<long long *>(g)[14] = same ? 1 : 0;
-    g[15] = 0.0;
+    // flags (64-bit integer) relative to the previous record of the same tile: bit 0 = same
+    // tesseroid (a further radial piece) -> the sweep keeps its whole angular half; bit 1 = same
+    // extent in longitude (bitwise equal w and e) -> it keeps the longitude part
+    long long flags = 0;
+    if ((qs % TVD_TILE) != 0) {
+        const int64_t tp = parent[sweep_piece[qs - 1]];
+        if (tp == t)
+            flags = 3;
+        else if (__double_as_longlong(tess_bounds[6 * tp + 0]) == __double_as_longlong(w) &&
+                 __double_as_longlong(tess_bounds[6 * tp + 1]) == __double_as_longlong(e))
+            flags = 2;
+    }
+    reinterpret_cast<long long *>(g)[14] = flags;
+    reinterpret_cast<long long *>(g)[15] = q;      // the piece's index in the model-order table
 }
 
 // Conservative far-field threshold.  The literal test (divisions, :135,140) splits iff
@@ -367,8 +474,8 @@ cudaError_t tvd_launch_pack_glq(const PieceTable &t, double *d_glq, double *d_ge
     const int threads = 128;
     const unsigned blocks = (unsigned)((t.n_pieces + threads - 1) / threads);
     k4_pack_glq<<<blocks, threads, 0, stream>>>(t.n_pieces, t.tess_bounds, t.tess_kind,
-                                                t.tess_params, t.top, t.bottom, t.parent, d_glq,
-                                                d_geom);
+                                                t.tess_params, t.top, t.bottom, t.parent,
+                                                t.sweep_piece, d_glq, d_geom);
     tvd_count_launch();
     return cudaGetLastError();
 }

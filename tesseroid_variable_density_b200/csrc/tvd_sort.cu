@@ -19,3 +19,16 @@ cudaError_t tvd_sort_keys(void *d_temp, size_t &temp_bytes, const unsigned long 
         tvd_count_launch(4);
     return err;
 }
+
+cudaError_t tvd_sort_pairs(void *d_temp, size_t &temp_bytes, const unsigned long long *keys_in,
+                           unsigned long long *keys_out, const int32_t *vals_in,
+                           int32_t *vals_out, int64_t n, cudaStream_t stream)
+{
+    if (n > 0x7fffffffLL)
+        return cudaErrorInvalidValue;
+    cudaError_t err = cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, keys_in, keys_out,
+                                                      vals_in, vals_out, (int)n, 0, 64, stream);
+    if (d_temp != nullptr)
+        tvd_count_launch(8);
+    return err;
+}
