@@ -353,6 +353,19 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
         out[s] = sum[s];
 }
 
+// acc += v if lhs > rhs, as one compare and one predicated add (the compiler's own code for
+// `if (far) acc += v` re-evaluates the compare, adds unconditionally and selects both halves)
+__device__ __forceinline__ void add_if_gt(double &acc, double v, double lhs, double rhs)
+{
+    asm("{\n"
+        ".reg .pred q;\n"
+        "setp.gt.f64 q, %2, %3;\n"
+        "@q add.f64 %0, %0, %1;\n"
+        "}\n"
+        : "+d"(acc)
+        : "d"(v), "d"(lhs), "d"(rhs));
+}
+
 template <int MASK, int THREADS, int MINBLOCKS, bool JAC>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 far_sweep(const FarArgs a)
@@ -472,14 +485,16 @@ far_sweep(const FarArgs a)
             }
 #pragma unroll
             for (int s = 0; s < NF; s++) {
-                const bool defer = !far[s] && valid;
-                const unsigned m = __ballot_sync(0xffffffffu, defer);
-                if (m) {
+                // hot path: one vote and one uniform branch.  Padding threads shadow a real point
+                // and are filtered out only inside the (rare) deferral branch.
+                if (__any_sync(0xffffffffu, !far[s])) {
+                    const bool defer = !far[s] && valid;
+                    const unsigned m = __ballot_sync(0xffffffffu, defer);
                     unsigned long long base = 0;
                     const int leader = __ffs(m) - 1;
-                    if (lane == leader)
+                    if (m != 0 && lane == leader)
                         base = atomicAdd(a.qcount + s, (unsigned long long)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
+                    base = __shfl_sync(0xffffffffu, base, leader & 31);
                     if (defer) {
                         const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
                         if (idx < a.qcap)
@@ -504,8 +519,7 @@ far_sweep(const FarArgs a)
             } else {
 #pragma unroll
                 for (int s = 0; s < NF; s++)
-                    if (far[s])
-                        acc[s] += v[s];
+                    add_if_gt(acc[s], v[s], NF == 1 ? t : t + trec[3 + s], pt.neg_r_sqr);
             }
         }
         __syncthreads();    // everyone is done with stage st
