@@ -380,9 +380,9 @@ def run_gpu(args):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if (achieved and peak > 0) else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this
-                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r1d.md);
+                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r1e.md);
                          # the algorithmic minimum is the piece records read once, 281 MB
-                         "traffic": 312.1e6 if P == 75776 else None,
+                         "traffic": 310.7e6 if P == 75776 else None,
                          "kernel": "far_sweep<gz>",
                          "kernel_ms_per_launch": far_ms / max(1, nfar.value),
                          "kernel_share_of_step": far_ms / ms,
