@@ -534,6 +534,91 @@ far_sweep(const FarArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Queue-only sweep: re-runs just the far tests and refills the near-field queues.  Used when
+// the queues of the main sweep overflowed: the far sums of that sweep are already complete (a
+// deferred pair is left out of them whether or not it found room in the queue), and the exact
+// queue sizes are known from its counters.
+// ---------------------------------------------------------------------------------------------
+template <int NF>
+__global__ void __launch_bounds__(TVD_FAR_THREADS)
+queue_sweep(const FarArgs a)
+{
+    constexpr int TREC = tvd_test_rec_len(NF);
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.y;
+    const int64_t q_begin = (int64_t)g * a.pieces_per_group;
+    int64_t q_end = q_begin + a.pieces_per_group;
+    if (q_end > a.n_pieces)
+        q_end = a.n_pieces;
+    const int64_t pidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = pidx < a.n_points;
+    const int64_t pi = valid ? pidx : 0;
+    const double lon = a.lon[pi], sinlat = a.sinlat[pi], coslat = a.coslat[pi], r = a.radius[pi];
+    double sl, cl;
+    sincos(lon, &sl, &cl);
+    const double r2 = 2.0 * r;
+    const double p2x = -r2 * (coslat * cl), p2y = -r2 * (coslat * sl), p2z = -r2 * sinlat;
+    const double neg_r_sqr = -(r * r);
+    for (int64_t q = q_begin; q < q_end; q++) {
+        const double *trec = a.test_rec + q * TREC;      // same address for every lane
+        // identical arithmetic to far_sweep, so the same pairs are deferred
+        double t;
+        if (NF == 1) {
+            t = fma(p2x, trec[0], trec[3]);
+            t = fma(p2y, trec[1], t);
+            t = fma(p2z, trec[2], t);
+        } else {
+            t = p2x * trec[0];
+            t = fma(p2y, trec[1], t);
+            t = fma(p2z, trec[2], t);
+        }
+#pragma unroll
+        for (int s = 0; s < NF; s++) {
+            const bool far = (NF == 1 ? t : t + trec[3 + s]) > neg_r_sqr;
+            if (__any_sync(0xffffffffu, !far)) {
+                const bool defer = !far && valid;
+                const unsigned m = __ballot_sync(0xffffffffu, defer);
+                unsigned long long base = 0;
+                const int leader = __ffs(m) - 1;
+                if (m != 0 && lane == leader)
+                    base = atomicAdd(a.qcount + s, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader & 31);
+                if (defer) {
+                    const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
+                    if (idx < a.qcap)
+                        a.queue[(unsigned long long)s * a.qcap + idx] =
+                            ((unsigned long long)pidx << 32) |
+                            (unsigned long long)reinterpret_cast<const long long *>(
+                                a.glq_rec + q * TVD_GLQ_REC)[15];
+                }
+            }
+        }
+    }
+}
+
+cudaError_t tvd_launch_queue_only(const FarArgs &a, cudaStream_t stream)
+{
+    if (a.n_points == 0 || a.n_pieces == 0)
+        return cudaSuccess;
+    int nf = 0;
+    for (int f = 0; f < TVD_NFIELDS; f++)
+        nf += (a.mask >> f) & 1;
+    dim3 grid((unsigned)((a.n_points + TVD_FAR_THREADS - 1) / TVD_FAR_THREADS),
+              (unsigned)a.n_groups);
+    switch (nf) {
+    case 1: queue_sweep<1><<<grid, TVD_FAR_THREADS, 0, stream>>>(a); break;
+    case 2: queue_sweep<2><<<grid, TVD_FAR_THREADS, 0, stream>>>(a); break;
+    case 3: queue_sweep<3><<<grid, TVD_FAR_THREADS, 0, stream>>>(a); break;
+    case 4: queue_sweep<4><<<grid, TVD_FAR_THREADS, 0, stream>>>(a); break;
+    case 5: queue_sweep<5><<<grid, TVD_FAR_THREADS, 0, stream>>>(a); break;
+    case 6: queue_sweep<6><<<grid, TVD_FAR_THREADS, 0, stream>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
 template <int MASK>
 static cudaError_t launch_mask(const FarArgs &a, cudaStream_t stream)
 {

@@ -227,6 +227,7 @@ struct FarArgs {
                                      // NaN marks a deferred pair; far_out is not written
 };
 cudaError_t tvd_launch_far(const FarArgs &a, cudaStream_t stream);
+cudaError_t tvd_launch_queue_only(const FarArgs &a, cudaStream_t stream);   // refill after overflow
 // sensitivity mode: rows of pieces -> rows of tesseroids, near-field terms added in piece order
 cudaError_t tvd_launch_jac_reduce(const PieceTable &t, int64_t n_points, const double *jac_pieces,
                                   int64_t n_pairs, const unsigned long long *keys,

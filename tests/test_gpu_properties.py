@@ -115,3 +115,20 @@ def test_shell_symmetry_at_scale():
     exact = analytical.shell_exponential_density(260e3, 0., -3e4, A, 10, 3300 - A)["gz"]
     assert np.max(np.abs(gz - exact)) <= 1e-3 * exact
     assert np.max(np.abs(gx)) <= 1e-3 * exact
+
+
+def test_queue_overflow_is_refilled_not_recomputed(big, monkeypatch):
+    """A near-field queue that is too small is rebuilt by a test-only sweep; values, counters
+    and the deferred pairs are those of a run with ample capacity."""
+    bounds, cc = big
+    dens = D.ExponentialDensity.between(-412, -275, 845.0, -5155.0, 3)
+    flat = flat_with(bounds, dens)
+    pm = PreparedModel(flat, delta=0.1)
+    want, swant = forward_raw("gz", *cc, pm, 2.5, return_stats=True)
+    pm.close()
+    assert swant["near_pairs"] > 1000
+    monkeypatch.setenv("TVD_DEBUG_QCAP", "1000")
+    pm = PreparedModel(flat, delta=0.1)
+    got, sgot = forward_raw("gz", *cc, pm, 2.5, return_stats=True)
+    pm.close()
+    assert np.array_equal(got, want) and sgot == swant
