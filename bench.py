@@ -390,7 +390,12 @@ def run_gpu(args):
                          "piece_pairs_per_launch": far_pairs / max(1, nfar.value),
                          "achieved_with_uncalibrated_v1_estimate_384": achieved_v1,
                          "peak_source": "DFMA microbenchmark run by this process "
-                                        "(MEASURED_PEAKS.json has no FP64 figure)"},
+                                        "(MEASURED_PEAKS.json has no FP64 figure)",
+                         # static facts of this kernel build from its ncu capture
+                         # (profiles/far_sweep_r1e.md); not measured by this run
+                         "ncu": {"fp64_pipe_pct_of_peak": 82.5, "issue_active_pct": 59.0,
+                                 "executed_fp64_instructions_per_piece_pair": 103.4,
+                                 "executed_flops_per_piece_pair": 146.6}},
             "e2e": {"value": float(n_tess) * P * args.steps * world / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": 4 * 8 * P, "d2h_bytes_per_step": 8 * P},
             "gpu_launches": launches, "clocks": clocks, "checksum": checksum,

@@ -38,7 +38,11 @@ def main():
     t_conv = time.perf_counter() - t0
     t0 = time.perf_counter()
     res, st = forward_raw("gz", *cc, pm, 2.5, njobs=a.gpus, return_stats=True)
+    dt_cold = time.perf_counter() - t0       # includes replicating the model to every GPU
+    t0 = time.perf_counter()
+    res, st = forward_raw("gz", *cc, pm, 2.5, njobs=a.gpus, return_stats=True)
     dt = time.perf_counter() - t0
+    print("first call (replicates the piece table to each GPU, packs records): %.2f s" % dt_cold)
     pairs = float(flat.size) * lons.size
     print("C4 full: %.3e pairs on %d GPU(s): model build %.2f s, coords %.2f s, forward %.2f s "
           "-> %.3e evals/s; near pairs %d, leaves/eval %.4f" % (

@@ -190,12 +190,15 @@ static int new_ctx(int device, DeviceCtx **out)
 // context of `device`, replicating the piece table from the host copy if needed
 static int get_ctx(tvd_model *m, int device, DeviceCtx **out)
 {
-    std::lock_guard<std::mutex> lock(m->mu);
-    auto it = m->ctx.find(device);
-    if (it != m->ctx.end()) {
-        *out = it->second;
-        return TVD_OK;
+    {
+        std::lock_guard<std::mutex> lock(m->mu);
+        auto it = m->ctx.find(device);
+        if (it != m->ctx.end()) {
+            *out = it->second;
+            return TVD_OK;
+        }
     }
+    // replicate outside the lock so that several devices are populated concurrently
     DeviceCtx *c = nullptr;
     int rc = new_ctx(device, &c);
     if (rc)
@@ -234,7 +237,16 @@ static int get_ctx(tvd_model *m, int device, DeviceCtx **out)
         return rc;
     }
     c->has_table = true;
-    m->ctx[device] = c;
+    {
+        std::lock_guard<std::mutex> lock(m->mu);
+        auto it = m->ctx.find(device);
+        if (it != m->ctx.end()) {       // another thread populated this device meanwhile
+            *out = it->second;
+            free_ctx(c);
+            return TVD_OK;
+        }
+        m->ctx[device] = c;
+    }
     *out = c;
     return TVD_OK;
 }

@@ -40,8 +40,7 @@ __device__ __forceinline__ void scale_nodes(double w, double e, double s, double
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
         o.lonc[i] = TVD_D2R * (0.5 * dlon * node + mlon);
         const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
-        o.sinlatc[i] = dd_sin(latc);
-        o.coslatc[i] = dd_cos(latc);
+        dd_sincos(latc, o.sinlatc[i], o.coslatc[i]);
         o.rc[i] = (0.5 * dr * node + mr);
     }
     o.scale = TVD_D2R * dlon * TVD_D2R * dlat * dr * 0.125;
@@ -61,10 +60,10 @@ __device__ double glq_literal(bool variable, int kind, const double *p, double l
     double result = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const double coslon = dd_cos(lon - nd.lonc[i]);
-        double sinlon = 0.0;
-        if (FIELD == TVD_GY || FIELD == TVD_GXY || FIELD == TVD_GYY || FIELD == TVD_GYZ)
-            sinlon = dd_sin(nd.lonc[i] - lon);
+        // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
+        double coslon, sinlon;
+        dd_sincos(lon - nd.lonc[i], sinlon, coslon);
+        sinlon = -sinlon;
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             const double kphi = coslat * nd.sinlatc[j] - sinlat * nd.coslatc[j] * coslon;

@@ -375,14 +375,17 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
     const double rt = 0.5 * (top + bottom) + TVD_R;
     const double lont = TVD_D2R * 0.5 * (w + e);
     const double latt = TVD_D2R * 0.5 * (s + n);
-    const double sinlatt = dd_sin(latt), coslatt = dd_cos(latt);
+    double sinlatt, coslatt, sinlont, coslont, sin_n, cos_n, sin_s, cos_s;
+    dd_sincos(latt, sinlatt, coslatt);
+    dd_sincos(lont, sinlont, coslont);
+    dd_sincos(TVD_D2R * n, sin_n, cos_n);
+    dd_sincos(TVD_D2R * s, sin_s, cos_s);
     const double rtop = top + TVD_R;
     const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * dd_cos(TVD_D2R * (e - w)));
-    const double Llat = rtop * acos(dd_sin(TVD_D2R * n) * dd_sin(TVD_D2R * s) +
-                                    dd_cos(TVD_D2R * n) * dd_cos(TVD_D2R * s));
+    const double Llat = rtop * acos(sin_n * sin_s + cos_n * cos_s);
     double *gm = geom + TVD_GEOM_REC * qs;
-    gm[0] = rt * (coslatt * dd_cos(lont));     // centre of the piece, geocentric Cartesian
-    gm[1] = rt * (coslatt * dd_sin(lont));
+    gm[0] = rt * (coslatt * coslont);          // centre of the piece, geocentric Cartesian
+    gm[1] = rt * (coslatt * sinlont);
     gm[2] = rt * sinlatt;
     gm[3] = rt * rt;
     gm[4] = fmax(Llon, Llat);                  // fmax ignores a single NaN (a NaN size never splits)
@@ -397,8 +400,7 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
         lonc[i] = TVD_D2R * (0.5 * dlon * node + mlon);
         const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
-        sinlatc[i] = dd_sin(latc);
-        coslatc[i] = dd_cos(latc);
+        dd_sincos(latc, sinlatc[i], coslatc[i]);
         rc[i] = (0.5 * dr * node + mr);
         rcsq[i] = rc[i] * rc[i];
         dens[i] = tvd_density_cr(kind, p, rc[i] - TVD_R);   // :274 (or the constant, :250)
