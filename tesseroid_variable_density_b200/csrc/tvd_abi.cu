@@ -485,21 +485,43 @@ extern "C" int tvd_model_get_pieces(const tvd_model *m, double *top, double *bot
 // ---------------------------------------------------------------------------------------------
 static int plan_groups(int64_t n_pieces, int64_t n_points_total)
 {
-    // Enough thread blocks for ~2 waves on 148 SMs, but never groups smaller than 4 tiles.
-    // Pure function of (Q, P_total).
+    // Pure function of (Q, P_total): every rank / device of a job derives the same plan.
+    //  - few points: split the piece table into enough groups for ~2 waves of blocks on 148 SMs,
+    //    but never groups smaller than 4 tiles;
+    //  - many points: one group, unless the last wave of blocks would leave most SMs idle; then
+    //    the smallest number of groups (<= 8) that fills the last wave to >= 97 %.
     const int64_t ppb = (int64_t)TVD_FAR_THREADS;
     const int64_t blocks_x = (n_points_total + ppb - 1) / ppb;
     if (blocks_x <= 0 || n_pieces <= 0)
         return 1;
-    const int64_t want = 148 * TVD_FAR_MINBLOCKS * 2;
-    int64_t g = (want + blocks_x - 1) / blocks_x;
-    const int64_t gmax = n_pieces / (4 * TVD_TILE);
+    const int64_t slots = 148 * TVD_FAR_MINBLOCKS;      // blocks resident at once
+    int64_t gmax = n_pieces / (4 * TVD_TILE);
+    if (gmax < 1)
+        gmax = 1;
+    if (gmax > 65535)
+        gmax = 65535;
+    int64_t g;
+    if (blocks_x < 2 * slots) {
+        g = (2 * slots + blocks_x - 1) / blocks_x;
+    } else {
+        g = 1;
+        double best = 0.0;
+        for (int64_t cand = 1; cand <= 8; cand++) {
+            const int64_t blocks = blocks_x * cand;
+            const int64_t waves = (blocks + slots - 1) / slots;
+            const double fill = (double)blocks / (double)(waves * slots);
+            if (fill > best + 1e-12) {
+                best = fill;
+                g = cand;
+            }
+            if (fill >= 0.97)
+                break;
+        }
+    }
     if (g > gmax)
         g = gmax;
     if (g < 1)
         g = 1;
-    if (g > 65535)
-        g = 65535;
     return (int)g;
 }
 
