@@ -25,7 +25,9 @@ __host__ __device__ constexpr int tvd_test_rec_len(int nf) { return ((3 + nf) + 
 #define TVD_MASK_G ((1 << TVD_GX) | (1 << TVD_GY) | (1 << TVD_GZ))
 #define TVD_MASK_TENSOR ((1 << TVD_GXX) | (1 << TVD_GXY) | (1 << TVD_GXZ) | (1 << TVD_GYY) | \
                          (1 << TVD_GYZ) | (1 << TVD_GZZ))
-#define TVD_TILE 64                         // pieces per shared-memory tile
+#ifndef TVD_TILE
+#define TVD_TILE 96                         // pieces per shared-memory tile (static smem <= 48 KB for 6 fused fields)
+#endif
 // far-field sweep launch shape: threads (= points) per block, resident blocks per SM
 #ifndef TVD_FAR_THREADS
 #define TVD_FAR_THREADS 512
