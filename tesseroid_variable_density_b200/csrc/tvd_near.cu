@@ -143,17 +143,43 @@ near_walk(const NearArgs a)
     stktop -= 1;                                          // pop of the root (:81)
     while (true) {
         nodes++;
-        // distance_n_size (:104-123).  These values only feed the split decision, where a last-bit
-        // difference matters only within ~1e-9 of the threshold: the fast sin/cos are used here,
-        // the double-double ones are kept for the integration nodes below.
-        const double lont = TVD_D2R * 0.5 * (w + e);
-        const double latt = TVD_D2R * 0.5 * (s + n);
-        const double sinlatt = tvd_sin(latt), coslatt = tvd_cos(latt);
-        const double cospsi = sinlat * sinlatt + coslat * coslatt * tvd_cos(lon - lont);
-        const double distance = sqrt(radius * radius + rt * rt - 2 * radius * rt * cospsi);
-        const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * tvd_cos(TVD_D2R * (e - w)));
-        const double Llat = rtop * acos(tvd_sin(TVD_D2R * n) * tvd_sin(TVD_D2R * s) +
-                                        tvd_cos(TVD_D2R * n) * tvd_cos(TVD_D2R * s));
+        // distance_n_size (:104-123).  The split decision compares d with ratio*L where, for the
+        // small cells of a deep subdivision, L = rtop*acos(1 - tiny) is dominated by rounding: the
+        // reference's decision is then reproduced only by reproducing its roundings, i.e. with
+        // correctly rounded sin/cos (double-double, slow).  The geometry is therefore evaluated
+        // with the fast sin/cos first and accepted when the decision is safe against the
+        // difference between the two evaluations; otherwise it is redone in double-double.
+        double distance, Llon, Llat;
+        {
+            const double lont = TVD_D2R * 0.5 * (w + e);
+            const double latt = TVD_D2R * 0.5 * (s + n);
+            const double sinlatt = tvd_sin(latt), coslatt = tvd_cos(latt);
+            const double cospsi = sinlat * sinlatt + coslat * coslatt * tvd_cos(lon - lont);
+            const double d2 = radius * radius + rt * rt - 2 * radius * rt * cospsi;
+            distance = sqrt(d2);
+            const double arg_lon = sinlatt * sinlatt + (coslatt * coslatt) * tvd_cos(TVD_D2R * (e - w));
+            const double arg_lat = tvd_sin(TVD_D2R * n) * tvd_sin(TVD_D2R * s) +
+                                   tvd_cos(TVD_D2R * n) * tvd_cos(TVD_D2R * s);
+            Llon = rtop * acos(arg_lon);
+            Llat = rtop * acos(arg_lat);
+            // relative uncertainties: 1-ulp differences in the trig values move the acos arguments
+            // by ~2e-16 absolute (L ~ sqrt(2 (1 - arg))) and d^2 by ~2 r rt 2e-16 ~ 0.02 m^2
+            const double u_d = 0.02 / d2 + 1e-9;
+            const double u_lon = 4e-16 / (1.0 - arg_lon), u_lat = 4e-16 / (1.0 - arg_lat);
+            const double tl = a.ratio * Llon, tt = a.ratio * Llat;
+            const bool safe = fabs(distance - tl) > (u_d + u_lon) * tl &&
+                              fabs(distance - tt) > (u_d + u_lat) * tt;
+            if (!safe) {      // also taken for NaN / zero sizes (comparisons false)
+                double sl, cl, sn, cn, ss, cs;
+                dd_sincos(latt, sl, cl);
+                dd_sincos(TVD_D2R * n, sn, cn);
+                dd_sincos(TVD_D2R * s, ss, cs);
+                const double cp = sinlat * sl + coslat * cl * dd_cos(lon - lont);
+                distance = sqrt(radius * radius + rt * rt - 2 * radius * rt * cp);
+                Llon = rtop * acos(sl * sl + (cl * cl) * dd_cos(TVD_D2R * (e - w)));
+                Llat = rtop * acos(sn * ss + cn * cs);
+            }
+        }
         // divisions (:129-146)
         int nlon = 1, nlat = 1;
         if (distance <= a.ratio * Llon) {
