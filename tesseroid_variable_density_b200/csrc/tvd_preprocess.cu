@@ -444,8 +444,9 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
 // Conservative far-field threshold.  The literal test (divisions, :135,140) splits iff
 // d <= ratio*Llon or d <= ratio*Llat (NaN sizes never split).  The sweep evaluates
 // d^2 = r^2 + rt^2 - 2 p.c from Cartesian position vectors with an absolute error far below
-// 1 m^2, so d2 > thr^2*(1+1e-9) + 2 guarantees that the literal test says "no split";
-// everything else is deferred to the literal walk.
+// 1 m^2, and the sizes L of root cells are reproduced to far better than 1e-6, so
+// d2 > thr^2*(1+2e-6) + 2 guarantees that the literal test says "no split"; everything else is
+// deferred to the literal walk.
 __global__ void __launch_bounds__(128)
 k4_pack_test(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios,
              double *__restrict__ test_rec)
@@ -461,7 +462,7 @@ k4_pack_test(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios
     tr[2] = gm[2];
     for (int f = 0; f < ratios.nf; f++) {
         const double thr = ratios.ratio[f] * gm[4];             // = max(ratio*Llon, ratio*Llat)
-        const double thr2 = thr * thr * (1.0 + 1e-9) + 2.0;     // NaN if both sizes are NaN
+        const double thr2 = thr * thr * (1.0 + 2e-6) + 2.0;     // NaN if both sizes are NaN
         tr[3 + f] = gm[3] - thr2;       // a NaN threshold defers every pair of the piece
     }
     for (int f = 3 + ratios.nf; f < trec; f++)
