@@ -289,10 +289,12 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
                 double y = 0.0, y3 = 0.0, y5 = 0.0, dx = 0.0, dy = 0.0, dz = 0.0;
                 if (T::needs_y5 || mask_has(MASK, TVD_POTENTIAL)) {
                     y = rsqrt_fast(l_sqr);
-                    if (T::needs_y3)
-                        y3 = y * y * y;
-                    if (T::needs_y5)
-                        y5 = y3 * y * y;
+                    if (T::needs_y3) {
+                        const double y2 = y * y;
+                        y3 = y2 * y;
+                        if (T::needs_y5)
+                            y5 = y3 * y2;
+                    }
                 } else {
                     y3 = rsqrt3_fast(l_sqr);       // gx, gy, gz only need l^-3
                 }
@@ -323,7 +325,7 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
                 // gradient tensor (Fatiando 0.5 integrands, z up)
                 if (mask_has(MASK, TVD_GXX)) {
                     double &acc = sum[mask_slot(MASK, TVD_GXX)];
-                    acc = fma(w * (3.0 * (dx * dx) - l_sqr), y5, acc);
+                    acc = fma(w * fma(3.0 * dx, dx, -l_sqr), y5, acc);
                 }
                 if (mask_has(MASK, TVD_GXY)) {
                     double &acc = sum[mask_slot(MASK, TVD_GXY)];
@@ -335,7 +337,7 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
                 }
                 if (mask_has(MASK, TVD_GYY)) {
                     double &acc = sum[mask_slot(MASK, TVD_GYY)];
-                    acc = fma(w * (3.0 * (dy * dy) - l_sqr), y5, acc);
+                    acc = fma(w * fma(3.0 * dy, dy, -l_sqr), y5, acc);
                 }
                 if (mask_has(MASK, TVD_GYZ)) {
                     double &acc = sum[mask_slot(MASK, TVD_GYZ)];
@@ -343,7 +345,7 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
                 }
                 if (mask_has(MASK, TVD_GZZ)) {
                     double &acc = sum[mask_slot(MASK, TVD_GZZ)];
-                    acc = fma(w * (3.0 * (dz * dz) - l_sqr), y5, acc);
+                    acc = fma(w * fma(3.0 * dz, dz, -l_sqr), y5, acc);
                 }
             }
         }
