@@ -416,9 +416,9 @@ extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int3
                           "(delta too small for this density)");
         return fail(status);
     }
-    if (total > 0xffffffffLL) {
+    if (total > 0x7fffffffLL) {
         cleanup_tmp();
-        set_error(TVD_ERR_TOO_MANY_PIECES, "tvd_model_create: more than 2^32-1 radial pieces");
+        set_error(TVD_ERR_TOO_MANY_PIECES, "tvd_model_create: more than 2^31-1 radial pieces");
         return fail(TVD_ERR_TOO_MANY_PIECES);
     }
     m->n_pieces = total;
