@@ -153,7 +153,8 @@ int tvd_forward(int field, tvd_model *model, int64_t n_points, const double *lon
  *   n_fields, fields, ratios   distinct tvd_field ids and the ratio D of each
  *   results      [n_fields][P] in the caller's field order, kernel units, OVERWRITTEN
  *   stats        NULL or int64[n_fields][TVD_NSTATS]
- * Compiled-in sets: any single field; {potential, gz, gzz}; {potential, gx, gy, gz};
+ * Compiled-in sets: any single field; {potential, gz}; {potential, gz, gzz};
+ * {potential, gx, gy, gz};
  * {gx, gy, gz}; the six tensor components.  Other sets return TVD_ERR_BAD_ARGUMENT
  * (tvd_fused_supported tells in advance).
  */

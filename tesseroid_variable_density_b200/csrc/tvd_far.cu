@@ -645,7 +645,8 @@ bool tvd_far_mask_supported(int mask)
     case TVD_M(TVD_POTENTIAL): case TVD_M(TVD_GX): case TVD_M(TVD_GY): case TVD_M(TVD_GZ):
     case TVD_M(TVD_GXX): case TVD_M(TVD_GXY): case TVD_M(TVD_GXZ): case TVD_M(TVD_GYY):
     case TVD_M(TVD_GYZ): case TVD_M(TVD_GZZ):
-    case TVD_MASK_V_GZ_GZZ: case TVD_MASK_V_G: case TVD_MASK_G: case TVD_MASK_TENSOR:
+    case TVD_MASK_V_GZ: case TVD_MASK_V_GZ_GZZ: case TVD_MASK_V_G: case TVD_MASK_G:
+    case TVD_MASK_TENSOR:
         return true;
     }
     return false;
@@ -666,6 +667,7 @@ cudaError_t tvd_launch_far(const FarArgs &a, cudaStream_t stream)
     case TVD_M(TVD_GYY): return launch_mask<TVD_M(TVD_GYY)>(a, stream);
     case TVD_M(TVD_GYZ): return launch_mask<TVD_M(TVD_GYZ)>(a, stream);
     case TVD_M(TVD_GZZ): return launch_mask<TVD_M(TVD_GZZ)>(a, stream);
+    case TVD_MASK_V_GZ: return launch_mask<TVD_MASK_V_GZ>(a, stream);
     case TVD_MASK_V_GZ_GZZ: return launch_mask<TVD_MASK_V_GZ_GZZ>(a, stream);
     case TVD_MASK_V_G: return launch_mask<TVD_MASK_V_G>(a, stream);
     case TVD_MASK_G: return launch_mask<TVD_MASK_G>(a, stream);

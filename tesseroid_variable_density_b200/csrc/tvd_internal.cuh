@@ -20,6 +20,7 @@ __host__ __device__ constexpr int tvd_test_rec_len(int nf) { return ((3 + nf) + 
 #define TVD_GLQ_REC 16
 #define TVD_MAX_FUSED 6                     // fields per fused sweep
 // fused field sets the sweep is compiled for (besides the ten single fields)
+#define TVD_MASK_V_GZ ((1 << TVD_POTENTIAL) | (1 << TVD_GZ))
 #define TVD_MASK_V_GZ_GZZ ((1 << TVD_POTENTIAL) | (1 << TVD_GZ) | (1 << TVD_GZZ))
 #define TVD_MASK_V_G ((1 << TVD_POTENTIAL) | (1 << TVD_GX) | (1 << TVD_GY) | (1 << TVD_GZ))
 #define TVD_MASK_G ((1 << TVD_GX) | (1 << TVD_GY) | (1 << TVD_GZ))

@@ -14,6 +14,7 @@ from tesseroid_variable_density_b200.tesseroid import (PreparedModel, _convert_c
 pytestmark = pytest.mark.gpu
 
 SETS = [
+    ["potential", "gz"],
     ["potential", "gz", "gzz"],
     ["potential", "gx", "gy", "gz"],
     ["gx", "gy", "gz"],
