@@ -73,3 +73,27 @@ def test_random_models_against_oracle(oracle_lib, seed, lon_mode, field, ratio):
     assert all(sg[k] == so[k] for k in KEYS)
     # tolerance 1e-9 (north_star) relative to the largest magnitude on the grid
     assert np.max(np.abs(g - o)) <= 1e-9 * np.max(np.abs(o))
+
+
+@pytest.mark.parametrize("seed", range(300, 312))
+def test_random_models_low_heights_large_ratios(oracle_lib, seed):
+    """Points 10 m .. 2 km (or 0.5 .. 50 km) above irregular models with ratios up to 8: deep
+    subdivisions everywhere.  Counts identical; values within 1e-8 (conditioning at tens of
+    metres above a cell: the reference's own output is that sensitive to its last bits)."""
+    rng = np.random.default_rng(seed)
+    flat = random_model(rng, 120, ["distinct", "columns", "same"][seed % 3])
+    npts = 150
+    lon = rng.uniform(-180, 360, npts)
+    lat = rng.uniform(-90, 90, npts)
+    h = rng.uniform(10.0, 2e3, npts) if seed % 2 else rng.uniform(500.0, 5e4, npts)
+    cc = _convert_coords(lon, lat, h)
+    delta = [0.1, 1e-2, None, 1e-3][seed % 4]
+    field, ratio = [("gz", 5.0), ("potential", 3.0), ("gx", 4.0), ("gy", 6.0), ("gz", 8.0)][seed % 5]
+    pm = PreparedModel(flat, delta=delta)
+    g, sg, cg = forward_raw(field, *cc, pm, ratio, leaf_counts=True)
+    pm.close()
+    o, so, co = oracle_lib.forward(field, flat.bounds, flat.kind, flat.params, delta, ratio, *cc,
+                                   leaf_counts=True, n_threads=8)
+    assert np.array_equal(cg, co)
+    assert all(sg[k] == so[k] for k in KEYS)
+    assert np.max(np.abs(g - o)) <= 1e-8 * np.max(np.abs(o))
