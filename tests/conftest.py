@@ -16,7 +16,22 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.dirname(os.path.abspath(__
         sys.path.insert(0, p)
 
 
+def _ensure_library_built():
+    """The tests load the in-tree libtvd.so; build it (nvcc cross-compiles without a GPU) if a
+    fresh checkout has not been through __graft_entry__.build() yet."""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "tesseroid_variable_density_b200", "csrc", "libtvd.so")
+    if os.path.isfile(lib):
+        return
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if os.path.isfile(nvcc):
+        subprocess.check_call(["bash", os.path.join(os.path.dirname(lib), "build.sh")],
+                              stdout=subprocess.DEVNULL)
+
+
 def pytest_configure(config):
+    _ensure_library_built()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: long golden replays (still part of the CPU suite)")
 
