@@ -197,3 +197,31 @@ def test_degenerate_and_tiny_inputs(oracle_lib):
                 assert rel <= 1e-7, rel       # 50 m above the cell: conditioning-limited
             else:
                 assert np.all(g == 0)
+
+
+def test_notebook_cases(oracle_lib):
+    """The two models of the reference's notebook (code/notebooks/tesseroid_density_example.ipynb,
+    cells 4-16): one tesseroid with an exponential density on a 51 x 51 grid at 260 km, and a
+    3 x 3 mesh mixing a constant, a linear and exponential densities at 50 km; all four fields."""
+    from tesseroid_variable_density_b200.mesher import Tesseroid
+    top, bottom = 0, -35000
+    rho0, rho1, b = 2670, 3300, 1e5
+    a = (rho1 - rho0) / (np.exp((abs(top - bottom)) / b) - 1)
+    c = rho0 - a
+    dens = D.ExponentialDensity(a, -1.0, 0.0, b, c)          # a*np.exp(-height/b) + c  (cell 6)
+    h = np.linspace(bottom, top, 11)
+    assert np.array_equal(dens(h), a * np.exp(-h / b) + c)
+    model = [Tesseroid(-0.1, 0.1, -0.1, 0.1, top, bottom, props={"density": dens})]
+    grid = gridder.regular((-5, 5, -5, 5), (51, 51), z=260000)
+    res = run_both(oracle_lib, model, grid, ["potential", "gx", "gy", "gz"], 1e-2, counts=False)
+    for field, (g, o, _, _, seq) in res.items():
+        assert seq and np.max(np.abs(g - o)) <= 1e-9 * np.max(np.abs(o)), field
+    mesh = TesseroidMesh((-1, 1, -1, 1, top, bottom), (1, 3, 3))
+    dl = [dens] * mesh.size
+    dl[0] = 500
+    dl[1] = D.LinearDensity(-0.01, 0.0, 0.0)                 # -0.01*height  (cell 12)
+    mesh.addprop("density", dl)
+    grid = gridder.regular((-5, 5, -5, 5), (51, 51), z=50000)
+    res = run_both(oracle_lib, mesh, grid, ["potential", "gx", "gy", "gz"], 1e-2, counts=True)
+    for field, (g, o, _, ceq, seq) in res.items():
+        assert ceq and seq and np.max(np.abs(g - o)) <= 1e-9 * np.max(np.abs(o)), field
