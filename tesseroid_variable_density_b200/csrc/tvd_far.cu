@@ -469,10 +469,10 @@ far_sweep(const FarArgs a)
         for (int qi = 0; qi < nq; qi++) {
             const double *trec = tt + qi * TREC;
             const double *grec = gg + qi * TVD_GLQ_REC;
-            // record flags (previous piece of the same tile): bit 0 = same tesseroid (a further
-            // radial piece) -> keep the whole angular half; bit 1 = same extent in longitude ->
-            // keep its longitude part.  Slot 15 = the piece's index in the model-order table.
-            const int flags = reinterpret_cast<const int2 *>(grec + 14)->x;
+            // record flags (previous piece of the same tile), two 32-bit words: x = same tesseroid
+            // (a further radial piece) -> keep the whole angular half; y = same extent in longitude
+            // -> keep its longitude part.  Slot 15 = the piece's index in the model-order table.
+            const int2 flags = *reinterpret_cast<const int2 *>(grec + 14);   // {same tesseroid, same lon}
             const long long q_model = reinterpret_cast<const long long *>(grec)[15];
             const double t = t_next;
             if (qi + 1 < nq)
@@ -507,9 +507,9 @@ far_sweep(const FarArgs a)
             }
             // every lane evaluates the root GLQ (it contains warp-wide votes); lanes whose pair
             // was deferred simply drop the value
-            if (!(flags & 2))
+            if (flags.y == 0)
                 glq_lon<MASK>(pt, grec, ang);
-            if (!(flags & 1))
+            if (flags.x == 0)
                 glq_lat<MASK>(pt, grec, ang);
             double v[NF];
             glq_radial<MASK>(pt, grec, ang, v);

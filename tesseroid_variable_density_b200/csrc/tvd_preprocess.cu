@@ -425,19 +425,22 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
             g[10 + 2 * j + k] = dens[k] * kappa * scale;
         }
     }
-    // flags (64-bit integer) relative to the previous record of the same tile: bit 0 = same
-    // tesseroid (a further radial piece) -> the sweep keeps its whole angular half; bit 1 = same
+    // flags relative to the previous record of the same tile, two 32-bit words: [0] = same
+    // tesseroid (a further radial piece) -> the sweep keeps its whole angular half; [1] = same
     // extent in longitude (bitwise equal w and e) -> it keeps the longitude part
-    long long flags = 0;
+    int same_tess = 0, same_lon = 0;
     if ((qs % TVD_TILE) != 0) {
         const int64_t tp = parent[sweep_piece[qs - 1]];
-        if (tp == t)
-            flags = 3;
-        else if (__double_as_longlong(tess_bounds[6 * tp + 0]) == __double_as_longlong(w) &&
-                 __double_as_longlong(tess_bounds[6 * tp + 1]) == __double_as_longlong(e))
-            flags = 2;
+        if (tp == t) {
+            same_tess = 1;
+            same_lon = 1;
+        } else if (__double_as_longlong(tess_bounds[6 * tp + 0]) == __double_as_longlong(w) &&
+                   __double_as_longlong(tess_bounds[6 * tp + 1]) == __double_as_longlong(e)) {
+            same_lon = 1;
+        }
     }
-    reinterpret_cast<long long *>(g)[14] = flags;
+    reinterpret_cast<int *>(g + 14)[0] = same_tess;
+    reinterpret_cast<int *>(g + 14)[1] = same_lon;
     reinterpret_cast<long long *>(g)[15] = q;      // the piece's index in the model-order table
 }
 
