@@ -231,3 +231,26 @@ def test_k1_tie_breaking_with_whole_periods(oracle_lib):
                 bad += 1
             pos += k
         assert bad == 0, "%d of %d tesseroids split differently at delta=%g" % (bad, n, delta)
+
+
+def test_plain_c_client_of_the_abi(tmp_path, oracle_lib):
+    """examples/c_abi_demo.c: the C ABI used from plain C (gcc), no Python in the loop; its
+    printed numbers must agree with the oracle."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "tesseroid_variable_density_b200", "csrc")
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.check_call(["gcc", "-O2", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "c_abi_demo.c"), "-o", exe, "-L", csrc,
+                           "-ltvd", "-lm", "-Wl,-rpath," + csrc])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    gz = float(re.search(r"gz at the centre point\s+(\S+)", out).group(1))
+    pot = float(re.search(r"potential at the centre\s+(\S+)", out).group(1))
+    mesh = TesseroidMesh((-1.5, 1.5, -1.5, 1.5, 0, -35000), (1, 3, 3))
+    mesh.addprop("density", [D.ExponentialDensity.between(2670, 3300, 0., -35000., 3)] * 9)
+    lats, lons, heights = gridder.regular((-2, 2, -2, 2), (5, 5), z=10e3)
+    want_gz = cases.OracleEngine(oracle_lib)("gz", lons, lats, heights, mesh, 2.5, 0.1)[12]
+    want_pot = cases.OracleEngine(oracle_lib)("potential", lons, lats, heights, mesh, 1, 0.1)[12]
+    assert abs(gz - want_gz) <= 1e-5 and abs(pot - want_pot) <= 1e-5      # printed with 6 decimals
