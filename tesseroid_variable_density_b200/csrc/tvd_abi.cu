@@ -77,7 +77,7 @@ struct DeviceCtx {
     bool glq_packed = false;
     int packed_nf = 0;
     double packed_ratio[TVD_MAX_FUSED] = {0};
-    Buf test_rec, glq_rec, geom;
+    Buf test_rec, glq_rec, geom, tile_rec;
     Buf far_out, queue, keys_sorted, pair_result, sort_temp, counters;
     Buf pts, result, counts, jac_pieces, jac_out;
     unsigned long long qcap_hint = 0;
@@ -119,6 +119,7 @@ static void free_ctx(DeviceCtx *c)
     c->test_rec.release();
     c->glq_rec.release();
     c->geom.release();
+    c->tile_rec.release();
     c->far_out.release();
     c->queue.release();
     c->keys_sorted.release();
@@ -585,8 +586,10 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
         for (int f = 0; f < TVD_MAX_FUSED; f++)
             rl.ratio[f] = f < nf ? fs.ratio[f] : 0.0;
         CUDA_TRY(c->test_rec.reserve((size_t)Q * tvd_test_rec_len(nf) * sizeof(double)));
+        CUDA_TRY(c->tile_rec.reserve((size_t)((Q + TVD_TILE - 1) / TVD_TILE) * TVD_TILE_REC *
+                                     sizeof(double)));
         CUDA_TRY(tvd_launch_pack_test(c->tab, c->geom.as<double>(), rl, c->test_rec.as<double>(),
-                                      stream));
+                                      c->tile_rec.as<double>(), stream));
         c->packed_nf = nf;
         for (int f = 0; f < nf; f++)
             c->packed_ratio[f] = fs.ratio[f];
@@ -624,6 +627,7 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
         fa.n_pieces = Q;
         fa.test_rec = c->test_rec.as<double>();
         fa.glq_rec = c->glq_rec.as<double>();
+        fa.tile_rec = c->tile_rec.as<double>();
         fa.n_groups = n_groups;
         fa.pieces_per_group = ppg;
         fa.far_out = c->far_out.as<double>();

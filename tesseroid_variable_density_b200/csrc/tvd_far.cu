@@ -465,63 +465,100 @@ far_sweep(const FarArgs a)
                 return fma(pt.p2z, trec[2], t);
             }
         };
-        double t_next = nq > 0 ? far_value(0) : 0.0;
-        for (int qi = 0; qi < nq; qi++) {
-            const double *trec = tt + qi * TREC;
-            const double *grec = gg + qi * TVD_GLQ_REC;
-            // record flags (previous piece of the same tile), two 32-bit words: x = same tesseroid
-            // (a further radial piece) -> keep the whole angular half; y = same extent in longitude
-            // -> keep its longitude part.  Slot 15 = the piece's index in the model-order table.
-            const int2 flags = *reinterpret_cast<const int2 *>(grec + 14);   // {same tesseroid, same lon}
-            const long long q_model = reinterpret_cast<const long long *>(grec)[15];
-            const double t = t_next;
-            if (qi + 1 < nq)
-                t_next = far_value(qi + 1);
-            bool far[NF];
-            if (NF == 1) {
-                far[0] = t > pt.neg_r_sqr;
-            } else {
+        // Tile-level test: if every lane of the warp is farther from the bounding sphere of the
+        // tile's piece centres than the tile's largest threshold (tvd_preprocess.cu:k4_pack_tiles),
+        // every per-pair test of the tile is known to pass: the tile is swept without tests,
+        // votes or predicated accumulation.  The far sums are the same either way.
+        bool tile_far = true;
+        {
+            const double *tr = a.tile_rec + ((q0 / TVD_TILE) * TVD_TILE_REC);
+            double tc = fma(pt.p2x, __ldg(tr + 0), __ldg(tr + 3));
+            tc = fma(pt.p2y, __ldg(tr + 1), tc);
+            tc = fma(pt.p2z, __ldg(tr + 2), tc);
+            const double d2c = tc - pt.neg_r_sqr;            // |p - C|^2
 #pragma unroll
-                for (int s = 0; s < NF; s++)
-                    far[s] = (t + trec[3 + s]) > pt.neg_r_sqr;
-            }
+            for (int s = 0; s < NF; s++)
+                tile_far = tile_far && (d2c > __ldg(tr + 4 + s));
+            tile_far = __all_sync(0xffffffffu, tile_far || !valid);
+        }
+        if (tile_far) {
+            for (int qi = 0; qi < nq; qi++) {
+                const double *grec = gg + qi * TVD_GLQ_REC;
+                const int2 flags = *reinterpret_cast<const int2 *>(grec + 14);
+                if (flags.y == 0)
+                    glq_lon<MASK>(pt, grec, ang);
+                if (flags.x == 0)
+                    glq_lat<MASK>(pt, grec, ang);
+                double v[NF];
+                glq_radial<MASK>(pt, grec, ang, v);
+                if (JAC) {
+                    if (valid)
+                        a.jac[reinterpret_cast<const long long *>(grec)[15] * a.n_points + pidx] = v[0];
+                } else {
 #pragma unroll
-            for (int s = 0; s < NF; s++) {
-                // hot path: one vote and one uniform branch.  Padding threads shadow a real point
-                // and are filtered out only inside the (rare) deferral branch.
-                if (__any_sync(0xffffffffu, !far[s])) {
-                    const bool defer = !far[s] && valid;
-                    const unsigned m = __ballot_sync(0xffffffffu, defer);
-                    unsigned long long base = 0;
-                    const int leader = __ffs(m) - 1;
-                    if (m != 0 && lane == leader)
-                        base = atomicAdd(a.qcount + s, (unsigned long long)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader & 31);
-                    if (defer) {
-                        const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
-                        if (idx < a.qcap)
-                            a.queue[(unsigned long long)s * a.qcap + idx] =
-                                ((unsigned long long)pidx << 32) | (unsigned long long)q_model;
-                    }
+                    for (int s = 0; s < NF; s++)
+                        acc[s] += v[s];
                 }
             }
-            // every lane evaluates the root GLQ (it contains warp-wide votes); lanes whose pair
-            // was deferred simply drop the value
-            if (flags.y == 0)
-                glq_lon<MASK>(pt, grec, ang);
-            if (flags.x == 0)
-                glq_lat<MASK>(pt, grec, ang);
-            double v[NF];
-            glq_radial<MASK>(pt, grec, ang, v);
-            if (JAC) {
-                // sensitivity mode: one value per (piece, point); NaN marks a deferred pair
-                if (valid)
-                    a.jac[q_model * a.n_points + pidx] =
-                        far[0] ? v[0] : __longlong_as_double(0x7ff8000000000000ll);
-            } else {
+        } else {
+            double t_next = nq > 0 ? far_value(0) : 0.0;
+            for (int qi = 0; qi < nq; qi++) {
+                const double *trec = tt + qi * TREC;
+                const double *grec = gg + qi * TVD_GLQ_REC;
+                // record flags (previous piece of the same tile), two 32-bit words: x = same tesseroid
+                // (a further radial piece) -> keep the whole angular half; y = same extent in longitude
+                // -> keep its longitude part.  Slot 15 = the piece's index in the model-order table.
+                const int2 flags = *reinterpret_cast<const int2 *>(grec + 14);   // {same tesseroid, same lon}
+                const long long q_model = reinterpret_cast<const long long *>(grec)[15];
+                const double t = t_next;
+                if (qi + 1 < nq)
+                    t_next = far_value(qi + 1);
+                bool far[NF];
+                if (NF == 1) {
+                    far[0] = t > pt.neg_r_sqr;
+                } else {
 #pragma unroll
-                for (int s = 0; s < NF; s++)
-                    add_if_gt(acc[s], v[s], NF == 1 ? t : t + trec[3 + s], pt.neg_r_sqr);
+                    for (int s = 0; s < NF; s++)
+                        far[s] = (t + trec[3 + s]) > pt.neg_r_sqr;
+                }
+#pragma unroll
+                for (int s = 0; s < NF; s++) {
+                    // hot path: one vote and one uniform branch.  Padding threads shadow a real point
+                    // and are filtered out only inside the (rare) deferral branch.
+                    if (__any_sync(0xffffffffu, !far[s])) {
+                        const bool defer = !far[s] && valid;
+                        const unsigned m = __ballot_sync(0xffffffffu, defer);
+                        unsigned long long base = 0;
+                        const int leader = __ffs(m) - 1;
+                        if (m != 0 && lane == leader)
+                            base = atomicAdd(a.qcount + s, (unsigned long long)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader & 31);
+                        if (defer) {
+                            const unsigned long long idx = base + __popc(m & ((1u << lane) - 1u));
+                            if (idx < a.qcap)
+                                a.queue[(unsigned long long)s * a.qcap + idx] =
+                                    ((unsigned long long)pidx << 32) | (unsigned long long)q_model;
+                        }
+                    }
+                }
+                // every lane evaluates the root GLQ (it contains warp-wide votes); lanes whose pair
+                // was deferred simply drop the value
+                if (flags.y == 0)
+                    glq_lon<MASK>(pt, grec, ang);
+                if (flags.x == 0)
+                    glq_lat<MASK>(pt, grec, ang);
+                double v[NF];
+                glq_radial<MASK>(pt, grec, ang, v);
+                if (JAC) {
+                    // sensitivity mode: one value per (piece, point); NaN marks a deferred pair
+                    if (valid)
+                        a.jac[q_model * a.n_points + pidx] =
+                            far[0] ? v[0] : __longlong_as_double(0x7ff8000000000000ll);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < NF; s++)
+                        add_if_gt(acc[s], v[s], NF == 1 ? t : t + trec[3 + s], pt.neg_r_sqr);
+                }
             }
         }
         __syncthreads();    // everyone is done with stage st

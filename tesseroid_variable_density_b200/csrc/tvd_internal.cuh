@@ -211,7 +211,10 @@ struct RatioList {
     double ratio[TVD_MAX_FUSED];
 };
 cudaError_t tvd_launch_pack_test(const PieceTable &t, const double *d_geom, RatioList ratios,
-                                 double *d_test, cudaStream_t stream);
+                                 double *d_test, double *d_tile, cudaStream_t stream);
+// per-tile record of the sweep: Cx Cy Cz |C|^2 lim_0 .. lim_5 (bounding sphere of the tile's piece
+// centres; a point farther than sqrt(lim_f) from C is far from every piece of the tile for field f)
+#define TVD_TILE_REC 10
 // Phase A: far-field sweep
 bool tvd_far_mask_supported(int mask);
 struct FarArgs {
@@ -219,7 +222,7 @@ struct FarArgs {
     int64_t n_points;
     const double *lon, *sinlat, *coslat, *radius;
     int64_t n_pieces;
-    const double *test_rec, *glq_rec;
+    const double *test_rec, *glq_rec, *tile_rec;
     int n_groups;
     int64_t pieces_per_group;
     double *far_out;                 // [nf][n_groups][n_points]

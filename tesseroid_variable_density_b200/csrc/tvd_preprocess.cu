@@ -472,6 +472,60 @@ k4_pack_test(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios
         tr[f] = 0.0;
 }
 
+// Tile records.  For the pieces of one tile: C = mean of their centres, R = largest distance of
+// a centre from C, thr_max_f = largest far-field threshold.  A point with
+//   |p - C| > R + thr_max_f (1 + 2e-6) + 3 m
+// satisfies d_pq >= |p - C| - R > thr_q (1 + 2e-6) + 3 for every piece q of the tile, hence
+// d_pq^2 > thr_q^2 (1 + 2e-6) + 2 + (rounding slack): every per-pair far test of the tile passes.
+__global__ void __launch_bounds__(128)
+k4_pack_tiles(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios,
+              double *__restrict__ tile_rec)
+{
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t q0 = tile * TVD_TILE;
+    if (q0 >= n_pieces)
+        return;
+    const int64_t q1 = q0 + TVD_TILE < n_pieces ? q0 + TVD_TILE : n_pieces;
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    for (int64_t q = q0; q < q1; q++) {
+        cx += geom[TVD_GEOM_REC * q + 0];
+        cy += geom[TVD_GEOM_REC * q + 1];
+        cz += geom[TVD_GEOM_REC * q + 2];
+    }
+    const double inv = 1.0 / (double)(q1 - q0);
+    cx *= inv;
+    cy *= inv;
+    cz *= inv;
+    double r2max = 0.0, lmax = 0.0;
+    bool bad = false;
+    for (int64_t q = q0; q < q1; q++) {
+        const double dx = geom[TVD_GEOM_REC * q + 0] - cx, dy = geom[TVD_GEOM_REC * q + 1] - cy;
+        const double dz = geom[TVD_GEOM_REC * q + 2] - cz;
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        const double L = geom[TVD_GEOM_REC * q + 4];
+        if (!(r2 == r2) || !(L == L))
+            bad = true;                     // NaN geometry: this tile always takes the per-pair path
+        r2max = fmax(r2max, r2);
+        lmax = fmax(lmax, L);
+    }
+    double *tr = tile_rec + TVD_TILE_REC * tile;
+    tr[0] = cx;
+    tr[1] = cy;
+    tr[2] = cz;
+    tr[3] = cx * cx + cy * cy + cz * cz;
+    const double R = sqrt(r2max) * (1.0 + 1e-9) + 1e-3;
+    for (int f = 0; f < TVD_MAX_FUSED; f++) {
+        double lim = __longlong_as_double(0x7ff0000000000000ll);        // +inf: never far
+        if (f < ratios.nf && !bad) {
+            const double x = R + ratios.ratio[f] * lmax * (1.0 + 2e-6) + 3.0;
+            lim = x * x * (1.0 + 1e-12) + 1.0;
+            if (!(lim == lim))
+                lim = __longlong_as_double(0x7ff0000000000000ll);
+        }
+        tr[4 + f] = lim;
+    }
+}
+
 cudaError_t tvd_launch_pack_glq(const PieceTable &t, double *d_glq, double *d_geom,
                                 cudaStream_t stream)
 {
@@ -487,14 +541,17 @@ cudaError_t tvd_launch_pack_glq(const PieceTable &t, double *d_glq, double *d_ge
 }
 
 cudaError_t tvd_launch_pack_test(const PieceTable &t, const double *d_geom, RatioList ratios,
-                                 double *d_test, cudaStream_t stream)
+                                 double *d_test, double *d_tile, cudaStream_t stream)
 {
     if (t.n_pieces == 0)
         return cudaSuccess;
     const int threads = 128;
     const unsigned blocks = (unsigned)((t.n_pieces + threads - 1) / threads);
     k4_pack_test<<<blocks, threads, 0, stream>>>(t.n_pieces, d_geom, ratios, d_test);
-    tvd_count_launch();
+    const int64_t n_tiles = (t.n_pieces + TVD_TILE - 1) / TVD_TILE;
+    k4_pack_tiles<<<(unsigned)((n_tiles + threads - 1) / threads), threads, 0, stream>>>(
+        t.n_pieces, d_geom, ratios, d_tile);
+    tvd_count_launch(2);
     return cudaGetLastError();
 }
 
