@@ -380,9 +380,9 @@ def run_gpu(args):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if (achieved and peak > 0) else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this
-                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r1e.md);
+                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r1f.md);
                          # the algorithmic minimum is the piece records read once, 281 MB
-                         "traffic": 310.7e6 if P == 75776 else None,
+                         "traffic": 312.9e6 if P == 75776 else None,
                          "kernel": "far_sweep<gz>",
                          "kernel_ms_per_launch": far_ms / max(1, nfar.value),
                          "kernel_share_of_step": far_ms / ms,
@@ -392,10 +392,10 @@ def run_gpu(args):
                          "peak_source": "DFMA microbenchmark run by this process "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          # static facts of this kernel build from its ncu capture
-                         # (profiles/far_sweep_r1e.md); not measured by this run
-                         "ncu": {"fp64_pipe_pct_of_peak": 82.5, "issue_active_pct": 59.0,
-                                 "executed_fp64_instructions_per_piece_pair": 103.4,
-                                 "executed_flops_per_piece_pair": 146.6}},
+                         # (profiles/far_sweep_r1f.md); not measured by this run
+                         "ncu": {"fp64_pipe_pct_of_peak": 87.7, "issue_active_pct": 59.0,
+                                 "executed_fp64_instructions_per_piece_pair": 100.4,
+                                 "executed_flops_per_piece_pair": 140.7}},
             "e2e": {"value": float(n_tess) * P * args.steps * world / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": 4 * 8 * P, "d2h_bytes_per_step": 8 * P},
             "gpu_launches": launches, "clocks": clocks, "checksum": checksum,
