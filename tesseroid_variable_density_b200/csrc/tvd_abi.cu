@@ -77,7 +77,9 @@ struct DeviceCtx {
     bool glq_packed = false;
     int packed_nf = 0;
     double packed_ratio[TVD_MAX_FUSED] = {0};
-    Buf test_rec, glq_rec, geom, tile_rec;
+    Buf test_rec, glq_rec, geom, tile_rec, ab_rec;
+    bool ab_packed = false;
+    double ab_radius = 0.0;
     Buf far_out, queue, keys_sorted, pair_result, sort_temp, counters;
     Buf pts, result, counts, jac_pieces, jac_out;
     unsigned long long qcap_hint = 0;
@@ -120,6 +122,7 @@ static void free_ctx(DeviceCtx *c)
     c->glq_rec.release();
     c->geom.release();
     c->tile_rec.release();
+    c->ab_rec.release();
     c->far_out.release();
     c->queue.release();
     c->keys_sorted.release();
@@ -594,11 +597,32 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
         for (int f = 0; f < nf; f++)
             c->packed_ratio[f] = fs.ratio[f];
     }
+    const int n_cnt = 8 + 8 * TVD_MAX_FUSED;
+    CUDA_TRY(c->counters.reserve(n_cnt * sizeof(unsigned long long)));
+    // points at one height: 2r*rc and r^2 + rc^2 per piece instead of per pair
+    const double *d_ab = nullptr;
+    if (!d_jac_out) {
+        int *d_flag = reinterpret_cast<int *>(c->counters.as<unsigned long long>() + 7);
+        int h_flag = 0;
+        double h_r0 = 0.0;
+        CUDA_TRY(tvd_launch_check_uniform(P, d_radius, d_flag, stream));
+        CUDA_TRY(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&h_r0, d_radius, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (h_flag == 1 && h_r0 == h_r0) {
+            if (!c->ab_packed || memcmp(&c->ab_radius, &h_r0, sizeof(double)) != 0) {
+                CUDA_TRY(c->ab_rec.reserve((size_t)Q * TVD_AB_REC * sizeof(double)));
+                CUDA_TRY(tvd_launch_pack_ab(c->tab, c->glq_rec.as<double>(), h_r0,
+                                            c->ab_rec.as<double>(), stream));
+                c->ab_packed = true;
+                c->ab_radius = h_r0;
+            }
+            d_ab = c->ab_rec.as<double>();
+        }
+    }
     CUDA_TRY(c->far_out.reserve((size_t)nf * n_groups * P * sizeof(double)));
     if (d_jac_out)
         CUDA_TRY(c->jac_pieces.reserve((size_t)Q * P * sizeof(double)));
-    const int n_cnt = 8 + 8 * TVD_MAX_FUSED;
-    CUDA_TRY(c->counters.reserve(n_cnt * sizeof(unsigned long long)));
     unsigned long long qcap = c->qcap_hint;
     if (qcap == 0) {
         qcap = 64ull * (unsigned long long)P;
@@ -628,6 +652,7 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
         fa.test_rec = c->test_rec.as<double>();
         fa.glq_rec = c->glq_rec.as<double>();
         fa.tile_rec = c->tile_rec.as<double>();
+        fa.ab_rec = d_ab;
         fa.n_groups = n_groups;
         fa.pieces_per_group = ppg;
         fa.far_out = c->far_out.as<double>();

@@ -247,18 +247,33 @@ __device__ __forceinline__ void glq_lat(const PointRegs &pt, const double *__res
 
 // The radial half: the eight nodes of one piece, all fields of the mask.  out[slot] receives the
 // piece's contribution to each field (kernel units, reference sign conventions).
-template <int MASK>
+template <int MASK, bool UR>
 __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__restrict__ g,
-                                           const Angular &A, double *__restrict__ out)
+                                           const double *__restrict__ ab, const Angular &A,
+                                           double *__restrict__ out)
 {
     typedef MaskTraits<MASK> T;
     const double2 rc = *reinterpret_cast<const double2 *>(g + 6);
     const double2 rcsq = *reinterpret_cast<const double2 *>(g + 8);
     const double2 w0 = *reinterpret_cast<const double2 *>(g + 10);   // w[0][0], w[0][1]
     const double2 w1 = *reinterpret_cast<const double2 *>(g + 12);   // w[1][0], w[1][1]
-    // r_sqr + rc_sqr - 2*radius*rc[k]*cospsi   (:247), no contraction
-    const double b[2] = {pt.r_sqr + rcsq.x, pt.r_sqr + rcsq.y};
-    const double a[2] = {pt.r2 * rc.x, pt.r2 * rc.y};
+    // r_sqr + rc_sqr - 2*radius*rc[k]*cospsi   (:247), no contraction.  When every point of the
+    // call has the same radius (a grid at one height), 2*radius*rc[k] and r_sqr + rc_sqr do not
+    // depend on the point and come precomputed (same roundings) with the tile.
+    double a[2], b[2];
+    if (UR) {
+        const double2 a01 = *reinterpret_cast<const double2 *>(ab + 0);
+        const double2 b01 = *reinterpret_cast<const double2 *>(ab + 2);
+        a[0] = a01.x;
+        a[1] = a01.y;
+        b[0] = b01.x;
+        b[1] = b01.y;
+    } else {
+        b[0] = pt.r_sqr + rcsq.x;
+        b[1] = pt.r_sqr + rcsq.y;
+        a[0] = pt.r2 * rc.x;
+        a[1] = pt.r2 * rc.y;
+    }
     const double rck[2] = {rc.x, rc.y};
     const double wjk[2][2] = {{w0.x, w0.y}, {w1.x, w1.y}};     // rho_k * kappa_jk * scale
     // field-specific node weights, same products as the reference's integrands
@@ -368,7 +383,7 @@ __device__ __forceinline__ void add_if_gt(double &acc, double v, double lhs, dou
         : "d"(v), "d"(lhs), "d"(rhs));
 }
 
-template <int MASK, int THREADS, int MINBLOCKS, bool JAC>
+template <int MASK, int THREADS, int MINBLOCKS, bool JAC, bool UR>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 far_sweep(const FarArgs a)
 {
@@ -377,6 +392,7 @@ far_sweep(const FarArgs a)
     constexpr int TREC = T::trec;
     __shared__ __align__(16) double s_test[2][TVD_TILE * TREC];
     __shared__ __align__(16) double s_glq[2][TVD_TILE * TVD_GLQ_REC];
+    __shared__ __align__(16) double s_ab[2][UR ? TVD_TILE * TVD_AB_REC : 2];
     __shared__ __align__(8) uint64_t s_bar[2];
 
     const int tid = threadIdx.x;
@@ -427,9 +443,12 @@ far_sweep(const FarArgs a)
             nq = TVD_TILE;
         const uint32_t bt = (uint32_t)(nq * TREC * sizeof(double));
         const uint32_t bg = (uint32_t)(nq * TVD_GLQ_REC * sizeof(double));
-        mbar_expect_tx(&s_bar[st], bt + bg);
+        const uint32_t ba = UR ? (uint32_t)(nq * TVD_AB_REC * sizeof(double)) : 0u;
+        mbar_expect_tx(&s_bar[st], bt + bg + ba);
         bulk_g2s(s_test[st], a.test_rec + q0 * TREC, bt, &s_bar[st]);
         bulk_g2s(s_glq[st], a.glq_rec + q0 * TVD_GLQ_REC, bg, &s_bar[st]);
+        if (UR)
+            bulk_g2s(s_ab[st], a.ab_rec + q0 * TVD_AB_REC, ba, &s_bar[st]);
     };
 
     if (tid == 0) {
@@ -446,6 +465,7 @@ far_sweep(const FarArgs a)
         int nq = (int)((q_end - q0) < TVD_TILE ? (q_end - q0) : TVD_TILE);
         const double *tt = s_test[st];
         const double *gg = s_glq[st];
+        const double *aa = s_ab[st];
         // d^2-part of the far test of piece qi, computed one piece ahead so that its dependent
         // FMA chain overlaps the radial work of the previous piece
         // conservative far-field test: d^2 - thr_f^2 = r^2 + (rt^2 - thr_f^2) - 2 p.c > 0 with
@@ -490,7 +510,7 @@ far_sweep(const FarArgs a)
                 if (flags.x == 0)
                     glq_lat<MASK>(pt, grec, ang);
                 double v[NF];
-                glq_radial<MASK>(pt, grec, ang, v);
+                glq_radial<MASK, UR>(pt, grec, aa + (UR ? qi * TVD_AB_REC : 0), ang, v);
                 if (JAC) {
                     if (valid)
                         a.jac[reinterpret_cast<const long long *>(grec)[15] * a.n_points + pidx] = v[0];
@@ -548,7 +568,7 @@ far_sweep(const FarArgs a)
                 if (flags.x == 0)
                     glq_lat<MASK>(pt, grec, ang);
                 double v[NF];
-                glq_radial<MASK>(pt, grec, ang, v);
+                glq_radial<MASK, UR>(pt, grec, aa + (UR ? qi * TVD_AB_REC : 0), ang, v);
                 if (JAC) {
                     // sensitivity mode: one value per (piece, point); NaN marks a deferred pair
                     if (valid)
@@ -665,11 +685,13 @@ static cudaError_t launch_mask(const FarArgs &a, cudaStream_t stream)
     dim3 grid((unsigned)((a.n_points + THREADS - 1) / THREADS), (unsigned)a.n_groups);
     if (a.jac != nullptr) {
         if constexpr (mask_count(MASK) == 1)
-            far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, true><<<grid, THREADS, 0, stream>>>(a);
+            far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, true, false><<<grid, THREADS, 0, stream>>>(a);
         else
             return cudaErrorInvalidValue;
+    } else if (a.ab_rec != nullptr) {
+        far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, false, true><<<grid, THREADS, 0, stream>>>(a);
     } else {
-        far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, false><<<grid, THREADS, 0, stream>>>(a);
+        far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, false, false><<<grid, THREADS, 0, stream>>>(a);
     }
     tvd_count_launch();
     return cudaGetLastError();

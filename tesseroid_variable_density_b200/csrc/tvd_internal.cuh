@@ -215,6 +215,13 @@ cudaError_t tvd_launch_pack_test(const PieceTable &t, const double *d_geom, Rati
 // per-tile record of the sweep: Cx Cy Cz |C|^2 lim_0 .. lim_5 (bounding sphere of the tile's piece
 // centres; a point farther than sqrt(lim_f) from C is far from every piece of the tile for field f)
 #define TVD_TILE_REC 10
+// points-at-one-height specialisation: per piece 2r*rc0 2r*rc1 r^2+rc0^2 r^2+rc1^2 (sweep order)
+#define TVD_AB_REC 4
+cudaError_t tvd_launch_pack_ab(const PieceTable &t, const double *d_glq, double radius,
+                               double *d_ab, cudaStream_t stream);
+// *d_flag = 1 if every radius[i] is bitwise equal to radius[0], else 0
+cudaError_t tvd_launch_check_uniform(int64_t n, const double *d_radius, int *d_flag,
+                                     cudaStream_t stream);
 // Phase A: far-field sweep
 bool tvd_far_mask_supported(int mask);
 struct FarArgs {
@@ -223,6 +230,7 @@ struct FarArgs {
     const double *lon, *sinlat, *coslat, *radius;
     int64_t n_pieces;
     const double *test_rec, *glq_rec, *tile_rec;
+    const double *ab_rec;            // non-NULL: all points share one radius (see TVD_AB_REC)
     int n_groups;
     int64_t pieces_per_group;
     double *far_out;                 // [nf][n_groups][n_points]

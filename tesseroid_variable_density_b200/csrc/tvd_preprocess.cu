@@ -597,3 +597,63 @@ cudaError_t tvd_debug_math_launch(int func, int64_t n, const double *d_x, double
     tvd_count_launch();
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// points-at-one-height specialisation of the far-field sweep
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k4_pack_ab(int64_t n_pieces, const double *__restrict__ glq_rec, double radius,
+           double *__restrict__ ab)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pieces)
+        return;
+    const double *g = glq_rec + TVD_GLQ_REC * q;
+    const double r_sqr = radius * radius;      // radius**2 (:239), as the sweep computes it
+    const double r2 = 2.0 * radius;            // 2*radius  (:247)
+    double *o = ab + TVD_AB_REC * q;
+    o[0] = r2 * g[6];
+    o[1] = r2 * g[7];
+    o[2] = r_sqr + g[8];
+    o[3] = r_sqr + g[9];
+}
+
+cudaError_t tvd_launch_pack_ab(const PieceTable &t, const double *d_glq, double radius,
+                               double *d_ab, cudaStream_t stream)
+{
+    if (t.n_pieces == 0)
+        return cudaSuccess;
+    k4_pack_ab<<<(unsigned)((t.n_pieces + 255) / 256), 256, 0, stream>>>(t.n_pieces, d_glq, radius,
+                                                                        d_ab);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void check_uniform(int64_t n, const double *__restrict__ radius, int *__restrict__ flag)
+{
+    const long long first = __double_as_longlong(radius[0]);
+    bool same = true;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        same = same && (__double_as_longlong(radius[i]) == first);
+    if (!same)
+        *flag = 0;
+}
+
+cudaError_t tvd_launch_check_uniform(int64_t n, const double *d_radius, int *d_flag,
+                                     cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), stream);
+    if (e != cudaSuccess || n == 0)
+        return e;
+    const int one = 1;
+    e = cudaMemcpyAsync(d_flag, &one, sizeof(int), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess)
+        return e;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 1184)
+        blocks = 1184;
+    check_uniform<<<blocks, 256, 0, stream>>>(n, d_radius, d_flag);
+    tvd_count_launch();
+    return cudaGetLastError();
+}

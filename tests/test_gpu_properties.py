@@ -132,3 +132,21 @@ def test_queue_overflow_is_refilled_not_recomputed(big, monkeypatch):
     got, sgot = forward_raw("gz", *cc, pm, 2.5, return_stats=True)
     pm.close()
     assert np.array_equal(got, want) and sgot == swant
+
+
+def test_one_height_specialisation_is_bit_exact(big):
+    """Points at one height take a sweep with 2r*rc and r^2 + rc^2 precomputed per piece; adding
+    one point at another height switches the specialisation off.  Same bits either way."""
+    bounds, cc = big
+    dens = D.ExponentialDensity.between(-412, -275, 845.0, -5155.0, 3)
+    pm = PreparedModel(flat_with(bounds, dens), delta=0.1)
+    n = 20000
+    lon, sinlat, coslat, radius = (c[:n].copy() for c in cc)
+    assert np.all(radius == radius[0])
+    uniform = forward_raw("gz", lon, sinlat, coslat, radius, pm, 2.5)
+    groups = _lib.load().tvd_plan_groups(pm.handle, n)
+    assert groups == _lib.load().tvd_plan_groups(pm.handle, n + 1)     # same summation plan
+    mixed = forward_raw("gz", np.append(lon, lon[0]), np.append(sinlat, sinlat[0]),
+                        np.append(coslat, coslat[0]), np.append(radius, radius[0] + 123.0), pm, 2.5)
+    assert np.array_equal(mixed[:n], uniform)
+    pm.close()
