@@ -41,8 +41,8 @@ NLAT = NLON = 1000
 SEED = 20190277
 # FP64 flops of one far-field gz (piece, point) pair, FMA = 2.
 #  * F_PAIR_EXECUTED: what the far-field sweep of THIS build executes per pair, from the ncu
-#    capture committed with it (profiles/far_sweep_r1f.md: 13.4 DADD + 46.7 DMUL + 40.3 DFMA =
-#    140.7 flops; smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on x elapsed cycles /
+#    capture committed with it (profiles/far_sweep_r1g.md: 11.4 DADD + 44.7 DMUL + 40.3 DFMA =
+#    136.7 flops; smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on x elapsed cycles /
 #    pairs).  `roofline.achieved` uses this figure: it is the hardware flop rate of the kernel
 #    and can be checked against ncu directly.  It must be re-measured when the kernel changes.
 #  * SURVEY.md section 8d (convention v1) ESTIMATED 384 = F_test 76 + F_glq 308 from guessed
@@ -51,7 +51,7 @@ SEED = 20190277
 #    Later kernels do the same pairs with fewer operations (cheaper test and cos, angular work
 #    shared between pieces), so rates computed with 218 or 384 exceed what the hardware executes;
 #    they are reported beside `achieved`, not as `achieved`.
-F_PAIR_EXECUTED = 140.7
+F_PAIR_EXECUTED = 136.7
 F_PAIR_CALIBRATED = 218
 F_PAIR_V1_ESTIMATE = 384
 
@@ -387,26 +387,26 @@ def run_gpu(args):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if (achieved and peak > 0) else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this
-                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r1f.md);
-                         # the algorithmic minimum is the piece records read once, 281 MB
-                         "traffic": 312.9e6 if P == 75776 else None,
+                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r1g.md);
+                         # the algorithmic minimum is the piece records read once, 337 MB
+                         "traffic": 370.1e6 if P == 75776 else None,
                          "kernel": "far_sweep<gz>",
                          "kernel_ms_per_launch": far_ms / max(1, nfar.value),
                          "kernel_share_of_step": far_ms / ms,
                          "flops_per_piece_pair": F_PAIR_EXECUTED,
                          "piece_pairs_per_launch": far_pairs / max(1, nfar.value),
                          # the instruction mix (DADD/DMUL count 1 flop, DFMA 2) caps the flop
-                         # fraction of a saturated FP64 pipe at 140.7 / (2 x 100.4) = 0.70
-                         "frac_ceiling_of_this_instruction_mix": 0.70,
+                         # fraction of a saturated FP64 pipe at 136.7 / (2 x 96.4) = 0.71
+                         "frac_ceiling_of_this_instruction_mix": 0.71,
                          "achieved_with_first_kernel_count_218": achieved_cal,
                          "achieved_with_survey_estimate_384": achieved_v1,
                          "peak_source": "DFMA microbenchmark run by this process "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          # static facts of this kernel build from its ncu capture
-                         # (profiles/far_sweep_r1f.md); not measured by this run
-                         "ncu": {"fp64_pipe_pct_of_peak": 87.7, "issue_active_pct": 59.0,
-                                 "executed_fp64_instructions_per_piece_pair": 100.4,
-                                 "executed_flops_per_piece_pair": 140.7}},
+                         # (profiles/far_sweep_r1g.md); not measured by this run
+                         "ncu": {"fp64_pipe_pct_of_peak": 86.8, "issue_active_pct": 59.9,
+                                 "executed_fp64_instructions_per_piece_pair": 96.4,
+                                 "executed_flops_per_piece_pair": 136.7}},
             "e2e": {"value": float(n_tess) * P * args.steps * world / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": 4 * 8 * P, "d2h_bytes_per_step": 8 * P},
             "gpu_launches": launches, "clocks": clocks, "checksum": checksum,
