@@ -1,21 +1,29 @@
 // tvd_far.cu -- Phase A: the far-field sweep (the dominant kernel), sm_100a FP64.
 //
-// One thread owns PPT computation points and walks the radial-piece table of its piece group.
-// Piece records are staged through shared memory in TVD_TILE-piece tiles by bulk asynchronous
-// copies (cp.async.bulk, i.e. the TMA 1-D path, completing on an mbarrier; double buffered) and
-// are read as broadcast LDS.128 (all lanes read the same record).  Per (piece, point):
+// One thread owns one computation point and walks the piece records of its piece group in
+// sweep order (tesseroids sorted by longitude extent, each followed by its radial pieces).
+// Records are staged through shared memory in TVD_TILE-piece tiles by bulk asynchronous copies
+// (cp.async.bulk, i.e. the TMA 1-D path, completing on an mbarrier; double buffered) and are read
+// as broadcast LDS.128 (all lanes read the same record).
 //
-//   1. conservative far-field test on the squared centre distance (9 FP64 ops, no sqrt, no
-//      libm): if it clears the threshold, the literal test of the reference
-//      (divisions, _tesseroid.pyx:129-146) is guaranteed to say "no split";
-//   2. far pairs: the 2x2x2 GLQ of the root cell (kernel*, _tesseroid.pyx:231-520) with the
-//      point-independent node data precomputed in the record; cos psi and l^2 keep the
-//      reference's operation order and are NOT contracted;
-//   3. every other pair is appended to the near-field queue (warp-aggregated atomic) and is
-//      walked literally by Phase B (tvd_near.cu).
+//   per tile      one test of the warp against the bounding sphere of the tile's pieces: if every
+//                 lane is beyond the tile's largest threshold, the tile is swept without
+//                 per-pair tests (the common case);
+//   per pair      otherwise a conservative far-field test on the squared centre distance
+//                 (3 DFMA + 1 DSETP, no sqrt, no libm): if it clears the threshold, the literal
+//                 test of the reference (divisions, _tesseroid.pyx:129-146) is guaranteed to say
+//                 "no split"; every other pair is appended to the near-field queue
+//                 (warp-aggregated atomic) and walked literally by Phase B (tvd_near.cu);
+//   far pairs     the 2x2x2 GLQ of the root cell (kernel*, _tesseroid.pyx:231-520) with the
+//                 point-independent node data precomputed in the record: its longitude part is
+//                 recomputed once per mesh column, its latitude part once per tesseroid, the
+//                 radial part per piece; cos psi and l^2 keep the reference's operation order
+//                 and are NOT contracted.
 //
-// The per-point sum over the pieces of a group is sequential in piece order; groups are summed
-// in group order by Phase C, so a point's value does not depend on how points are sharded.
+// The kernel is compiled for a mask of fields (single fields and a few fused sets), for the
+// sensitivity mode (JAC) and for points at one height (UR).  The per-point sum over the pieces of
+// a group is sequential in sweep order; groups are summed in group order by Phase C, so a point's
+// value does not depend on how points are sharded.
 #include "tvd_internal.cuh"
 
 // ---------------------------------------------------------------------------------------------
