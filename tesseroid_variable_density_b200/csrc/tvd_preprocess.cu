@@ -3,9 +3,11 @@
 // K1  density-based radial discretisation, one thread per tesseroid
 //     (reference: _density_based_discretization / _divider_calculation,
 //      code/tesseroid_density/tesseroid.py:237-300; NumPy semantics restated literally)
-// K4  per-piece root records for the far-field sweep: the point-independent halves of
-//     distance_n_size (_tesseroid.pyx:104-123) and scale_nodes (:152-176), the density at the
-//     radial GLQ nodes (:274) and the field-specific node weights.
+// --  sweep order: tesseroids stably sorted by longitude extent (tvd_build_sweep_order)
+// K4  per-piece root records for the far-field sweep, in sweep order: the point-independent
+//     halves of distance_n_size (_tesseroid.pyx:104-123) and scale_nodes (:152-176), the density
+//     at the radial GLQ nodes (:274), the node weights, the far-test records per ratio set, the
+//     bounding spheres of the tiles and the per-piece constants of the one-height specialisation.
 #include "tvd_internal.cuh"
 
 // ---------------------------------------------------------------------------------------------
