@@ -192,6 +192,14 @@ int tvd_forward_device(int field, tvd_model *model, int device, int64_t n_points
                        const double *d_radius, double ratio, int stack_size, int n_groups,
                        double *d_result, int64_t *stats, void *stream);
 
+/* tvd_forward_fused with DEVICE-resident points and results on `device` (the rank-per-GPU form of
+ * the fused sweep): d_results[i] is the device array of the caller's i-th field. */
+int tvd_forward_fused_device(int n_fields, const int *fields, const double *ratios,
+                             tvd_model *model, int device, int64_t n_points,
+                             const double *d_lon_rad, const double *d_sinlat,
+                             const double *d_coslat, const double *d_radius, int stack_size,
+                             int n_groups, double *const *d_results, int64_t *stats, void *stream);
+
 /* The n_groups that tvd_forward would choose for a job of n_points_total points over this model
  * (pure function of its arguments; lets independent ranks agree on the summation plan). */
 int tvd_plan_groups(const tvd_model *model, int64_t n_points_total);

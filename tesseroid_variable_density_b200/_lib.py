@@ -43,6 +43,10 @@ SIGNATURES = {
                                     _dp, _dp, _dp, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _lp]),
     "tvd_sensitivity": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, C.c_double,
                                   C.c_int, C.c_int, _dp, _lp]),
+    "tvd_forward_fused_device": (C.c_int, [C.c_int, C.POINTER(C.c_int), _dp, C.c_void_p, C.c_int,
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                           _lp, C.c_void_p]),
     "tvd_fused_supported": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "tvd_forward_device": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int,

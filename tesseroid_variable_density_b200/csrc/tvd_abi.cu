@@ -831,6 +831,40 @@ extern "C" int tvd_forward_device(int field, tvd_model *m, int device, int64_t n
                         n_groups, res, stats, nullptr, (cudaStream_t)stream);
 }
 
+extern "C" int tvd_forward_fused_device(int n_fields, const int *fields, const double *ratios,
+                                        tvd_model *m, int device, int64_t n_points,
+                                        const double *d_lon, const double *d_sinlat,
+                                        const double *d_coslat, const double *d_radius,
+                                        int stack_size, int n_groups, double *const *d_results,
+                                        int64_t *stats, void *stream)
+{
+    g_last_error.clear();
+    if (!m || n_points < 0 || !d_results)
+        return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_forward_fused_device: bad argument");
+    FieldSet fs;
+    int order[TVD_MAX_FUSED];
+    int rc = make_field_set(n_fields, fields, ratios, fs, order);
+    if (rc)
+        return rc;
+    DeviceCtx *c = nullptr;
+    rc = get_ctx(m, device, &c);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_TRY(cudaSetDevice(device));
+    double *res[TVD_MAX_FUSED];
+    for (int i = 0; i < n_fields; i++)
+        res[order[i]] = d_results[i];
+    std::vector<int64_t> st((size_t)n_fields * TVD_NSTATS, 0);
+    rc = forward_core(m, c, fs, n_points, d_lon, d_sinlat, d_coslat, d_radius, stack_size, n_groups,
+                      res, st.data(), nullptr, (cudaStream_t)stream);
+    if (!rc && stats)
+        for (int i = 0; i < n_fields; i++)
+            memcpy(stats + (size_t)i * TVD_NSTATS, st.data() + (size_t)order[i] * TVD_NSTATS,
+                   TVD_NSTATS * sizeof(int64_t));
+    return rc;
+}
+
 // one device's share of tvd_forward: host slices in, host slices out
 static int forward_host_slice(tvd_model *m, int device, const FieldSet &fs, const int *order,
                               int n_fields, int64_t P, int64_t p0, int64_t P_total,

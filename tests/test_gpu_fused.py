@@ -77,3 +77,32 @@ def test_fields_api():
     assert not fused_supported(["gx", "gzz"])
     out = tesseroid.fields(["gx", "gzz"], lons, lats, heights, mesh, delta=0.1)
     assert np.array_equal(out["gzz"], tesseroid.gzz(lons, lats, heights, mesh, delta=0.1))
+
+
+def test_fused_device_entry_point():
+    """tvd_forward_fused_device (device-resident points and results) = the host entry point."""
+    import ctypes as C
+    import torch
+    from tesseroid_variable_density_b200 import _lib
+    lib = _lib.load()
+    mesh = cases.exponential_case(1e4, 10)[0]
+    lats, lons, heights = cases.GRIDS["global2km"]()
+    cc = _convert_coords(lons, lats, heights)
+    pm = PreparedModel(mesh, delta=0.1)
+    names, ratios = ["gzz", "potential", "gz"], [8.0, 1.0, 2.5]
+    want = forward_raw_fused(names, *cc, pm, ratios)
+    n = lons.size
+    d = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for c in cc]
+    out = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in names]
+    ids = (C.c_int * 3)(*[_lib.FIELDS[f] for f in names])
+    rat = np.ascontiguousarray(ratios, dtype=np.float64)
+    ptrs = (C.c_void_p * 3)(*[o.data_ptr() for o in out])
+    stats = np.zeros((3, _lib.NSTATS), dtype=np.int64)
+    rc = lib.tvd_forward_fused_device(3, ids, _lib.ptr_f64(rat), pm.handle, 0, n, d[0].data_ptr(),
+                                      d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), 200,
+                                      lib.tvd_plan_groups(pm.handle, n), ptrs, _lib.ptr_i64(stats),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    for f, o in zip(names, out):
+        assert np.array_equal(o.cpu().numpy(), want[f]), f
+    pm.close()
