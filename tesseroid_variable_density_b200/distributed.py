@@ -63,3 +63,42 @@ def forward_sharded(field, lon_rad, sinlat, coslat, radius, compute, group=None,
         s, e = shard_bounds(n, world, r)
         out[s:e] = parts[r][:e - s].cpu().numpy()
     return out
+
+
+def make_gpu_compute(prepared, ratio, n_points_total, device=None):
+    """
+    `compute` callable for :func:`forward_sharded`: evaluates a chunk of points on this rank's
+    GPU through ``tvd_forward_device`` with the summation plan of the WHOLE job
+    (``tvd_plan_groups(model, n_points_total)``), so that the gathered result is bit-identical
+    to a single-GPU run of all points.  `prepared` is a
+    :class:`~tesseroid_variable_density_b200.tesseroid.PreparedModel` built on that GPU.
+    """
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+    from .tesseroid import STACK_SIZE
+
+    lib = _lib.load()
+    if device is None:
+        device = torch.cuda.current_device()
+    n_groups = lib.tvd_plan_groups(prepared.handle, int(n_points_total))
+
+    def compute(field, lon_rad, sinlat, coslat, radius):
+        n = int(np.asarray(lon_rad).size)
+        dev = torch.device("cuda", device)
+        pts = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+               for a in (lon_rad, sinlat, coslat, radius)]
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        stats = np.zeros(_lib.NSTATS, dtype=np.int64)
+        stream = torch.cuda.current_stream(dev)
+        rc = lib.tvd_forward_device(_lib.FIELDS[field], prepared.handle, int(device), n,
+                                    pts[0].data_ptr(), pts[1].data_ptr(), pts[2].data_ptr(),
+                                    pts[3].data_ptr(), float(ratio), int(STACK_SIZE), n_groups,
+                                    out.data_ptr(), _lib.ptr_i64(stats),
+                                    C.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "tvd_forward_device")
+        return out.cpu().numpy()
+
+    return compute
