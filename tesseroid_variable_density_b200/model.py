@@ -65,38 +65,45 @@ def _check_bounds(bounds):
         raise AssertionError("Invalid tesseroid dimensions {}".format(list(bounds[bad])))
 
 
+def _is_number(d):
+    return isinstance(d, (numbers.Real, np.floating, np.integer)) and not isinstance(d, bool)
+
+
 def _densities_to_arrays(dens_seq, n):
     """kind/params arrays (and a keep mask) for a per-cell density sequence of length n."""
+    keep = np.ones(n, dtype=bool)
     if isinstance(dens_seq, DensityTable):
         assert len(dens_seq) == n
-        return dens_seq.kind, dens_seq.params, np.ones(n, dtype=bool)
-    try:
-        arr = np.asarray(dens_seq)
-    except Exception:  # ragged / exotic sequences
-        arr = None
-    if arr is not None and arr.dtype != object and arr.shape == (n,) and \
-            np.issubdtype(arr.dtype, np.number):
-        params = np.zeros((n, _density.NPAR))
-        params[:, 0] = arr
-        return np.zeros(n, dtype=np.int32), params, np.ones(n, dtype=bool)
-    # general per-cell objects: convert each distinct object once
-    kind = np.empty(n, dtype=np.int32)
-    params = np.zeros((n, _density.NPAR))
-    cache = {}
-    for i in range(n):
-        d = dens_seq[i]
-        if isinstance(d, (numbers.Real, np.floating, np.integer)) and not isinstance(d, bool):
-            kind[i] = _density.CONST
-            params[i, 0] = d
-            continue
-        key = id(d)
-        kp = cache.get(key)
-        if kp is None:
-            kp = _density.as_kind_params(d)
-            cache[key] = kp
-        kind[i] = kp[0]
-        params[i] = kp[1]
-    return kind, params, np.ones(n, dtype=bool)
+        return dens_seq.kind, dens_seq.params, keep
+    if n == 0:
+        return np.zeros(0, dtype=np.int32), np.zeros((0, _density.NPAR)), keep
+    # all numbers: constant densities, vectorised
+    if isinstance(dens_seq, np.ndarray) and dens_seq.dtype != object:
+        if dens_seq.shape == (n,) and np.issubdtype(dens_seq.dtype, np.number):
+            params = np.zeros((n, _density.NPAR))
+            params[:, 0] = dens_seq
+            return np.zeros(n, dtype=np.int32), params, keep
+    elif _is_number(dens_seq[0]):
+        try:
+            arr = np.array(dens_seq, dtype=np.float64)
+        except (TypeError, ValueError):
+            arr = None
+        if arr is not None and arr.shape == (n,):
+            params = np.zeros((n, _density.NPAR))
+            params[:, 0] = arr
+            return np.zeros(n, dtype=np.int32), params, keep
+    # objects: convert every DISTINCT object once (a mesh of a million cells usually shares a
+    # handful of density objects) and scatter with NumPy
+    ids = np.fromiter((id(d) for d in dens_seq), dtype=np.int64, count=n)
+    uniq, first, inverse = np.unique(ids, return_index=True, return_inverse=True)
+    tab_kind = np.empty(uniq.size, dtype=np.int32)
+    tab_params = np.zeros((uniq.size, _density.NPAR))
+    for u, i in enumerate(first):
+        k, p = _density.as_kind_params(dens_seq[int(i)])
+        tab_kind[u] = k
+        tab_params[u] = p
+    inverse = inverse.reshape(-1)
+    return tab_kind[inverse], tab_params[inverse], keep
 
 
 def flatten_model(model, dens=None):
