@@ -212,6 +212,12 @@ int64_t tvd_launch_count(int reset);
  * sweep) accumulated since the last reset, and the number of launches it covers. */
 double tvd_far_kernel_ms(int reset, int64_t *n_launches);
 
+/* Device time (ms, CUDA events on the launching stream) by phase, accumulated since the last
+ * reset: out[0] far-field sweeps, out[1] near-field walks (rediscretizer proper,
+ * _tesseroid.pyx:34-98), out[2] everything enqueued after the sweep (key sort, walks, combine),
+ * out[3] number of sweeps.  tvd_far_kernel_ms resets the same counters. */
+void tvd_phase_ms(int reset, double *out);
+
 /* FP64 peak probe: runs a dependent-chain-free DFMA loop on `device` and returns the measured
  * FP64 rate in TFLOP/s (FMA = 2 flops).  Roofline denominator, see DESIGN.md. */
 double tvd_measure_fp64_peak(int device, int iters);
@@ -222,7 +228,9 @@ double tvd_measure_fp64_peak(int device, int iters);
 int tvd_debug_trig(int device, int64_t n, const double *x, double *cos_out, double *sin_out);
 
 /* Debug/test hook: the double-double sin (func 0), cos (1) and exp (2) that K1 uses for the
- * density samples (tesseroid.py:259,294), evaluated on `device` for n host values. */
+ * density samples (tesseroid.py:259,294), and the table-based correctly rounded sin (3), cos (4)
+ * and sincos (5: its sine, 6: its cosine) of the near-field walk (the values glibc returned to
+ * the reference at _tesseroid.pyx:113-121,168-169,242), evaluated on `device` for n host values. */
 int tvd_debug_math(int device, int func, int64_t n, const double *x, double *out);
 
 #ifdef __cplusplus

@@ -54,6 +54,7 @@ SIGNATURES = {
     "tvd_plan_groups": (C.c_int, [C.c_void_p, C.c_int64]),
     "tvd_launch_count": (C.c_int64, [C.c_int]),
     "tvd_far_kernel_ms": (C.c_double, [C.c_int, _lp]),
+    "tvd_phase_ms": (None, [C.c_int, _dp]),
     "tvd_measure_fp64_peak": (C.c_double, [C.c_int, C.c_int]),
     "tvd_debug_trig": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp]),
     "tvd_debug_math": (C.c_int, [C.c_int, C.c_int, C.c_int64, _dp, _dp]),

@@ -8,7 +8,11 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fa
 mkdir -p _obj
 pids=()
 for f in tvd_preprocess tvd_far tvd_near tvd_sort tvd_abi; do
-  if [ ! -f _obj/$f.o ] || [ $f.cu -nt _obj/$f.o ] || [ tvd_internal.cuh -nt _obj/$f.o ] || [ ../../include/tvd.h -nt _obj/$f.o ]; then
+  stale=0
+  for dep in $f.cu tvd_internal.cuh tvd_ddmath.cuh tvd_crtrig.cuh tvd_sincos_table.inc ../../include/tvd.h build.sh; do
+    if [ ! -f _obj/$f.o ] || [ $dep -nt _obj/$f.o ]; then stale=1; fi
+  done
+  if [ $stale = 1 ]; then
     ( $NVCC $FLAGS -c $f.cu -o _obj/$f.o > _obj/$f.log 2>&1 || { cat _obj/$f.log; exit 1; } ) &
     pids+=($!)
   fi

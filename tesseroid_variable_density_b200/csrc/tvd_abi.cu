@@ -21,6 +21,7 @@ static std::atomic<int64_t> g_launches{0};
 static std::mutex g_far_mu;
 static double g_far_ms = 0.0;
 static int64_t g_far_launches = 0;
+static double g_near_ms = 0.0, g_post_ms = 0.0;     // near-field walks; everything after the sweep
 
 void tvd_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -85,6 +86,7 @@ struct DeviceCtx {
     unsigned long long qcap_hint = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_near[2 * TVD_MAX_FUSED] = {nullptr}, ev_end = nullptr;
     std::mutex mu;
 };
 
@@ -138,6 +140,11 @@ static void free_ctx(DeviceCtx *c)
         cudaEventDestroy(c->ev0);
     if (c->ev1)
         cudaEventDestroy(c->ev1);
+    for (cudaEvent_t ev : c->ev_near)
+        if (ev)
+            cudaEventDestroy(ev);
+    if (c->ev_end)
+        cudaEventDestroy(c->ev_end);
     if (c->stream)
         cudaStreamDestroy(c->stream);
     delete c;
@@ -183,6 +190,10 @@ static int new_ctx(int device, DeviceCtx **out)
         e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess)
         e = cudaEventCreate(&c->ev1);
+    for (int i = 0; i < 2 * TVD_MAX_FUSED && e == cudaSuccess; i++)
+        e = cudaEventCreate(&c->ev_near[i]);
+    if (e == cudaSuccess)
+        e = cudaEventCreate(&c->ev_end);
     if (e != cudaSuccess) {
         free_ctx(c);
         CUDA_TRY(e);
@@ -284,10 +295,25 @@ extern "C" double tvd_far_kernel_ms(int reset, int64_t *n_launches)
     if (n_launches)
         *n_launches = g_far_launches;
     if (reset) {
-        g_far_ms = 0.0;
+        g_far_ms = g_near_ms = g_post_ms = 0.0;
         g_far_launches = 0;
     }
     return ms;
+}
+
+extern "C" void tvd_phase_ms(int reset, double *out)
+{
+    std::lock_guard<std::mutex> lock(g_far_mu);
+    if (out) {
+        out[0] = g_far_ms;
+        out[1] = g_near_ms;
+        out[2] = g_post_ms;
+        out[3] = (double)g_far_launches;
+    }
+    if (reset) {
+        g_far_ms = g_near_ms = g_post_ms = 0.0;
+        g_far_launches = 0;
+    }
 }
 
 extern "C" double tvd_measure_fp64_peak(int device, int iters)
@@ -327,7 +353,7 @@ extern "C" int tvd_debug_trig(int device, int64_t n, const double *x, double *co
 extern "C" int tvd_debug_math(int device, int func, int64_t n, const double *x, double *out)
 {
     g_last_error.clear();
-    if (n < 0 || func < 0 || func > 2 || (n > 0 && (!x || !out)))
+    if (n < 0 || func < 0 || func > 6 || (n > 0 && (!x || !out)))
         return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_debug_math: bad argument");
     if (tvd_device_count() <= device || device < 0)
         return set_error(TVD_ERR_NO_DEVICE, "tvd_debug_math: no such CUDA device");
@@ -723,7 +749,9 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
             na.counters = d_cnt + 8 + 8 * f;
             na.leaf_counts = d_leaf_counts;
             na.n_points = P;
+            CUDA_TRY(cudaEventRecord(c->ev_near[2 * f], stream));
             CUDA_TRY(tvd_launch_near(na, stream));
+            CUDA_TRY(cudaEventRecord(c->ev_near[2 * f + 1], stream));
         }
         if (d_jac_out)
             CUDA_TRY(tvd_launch_jac_reduce(c->tab, P, c->jac_pieces.as<double>(), (int64_t)n,
@@ -737,7 +765,21 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
     }
     unsigned long long h_cnt[8 + 8 * TVD_MAX_FUSED];
     CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(c->ev_end, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    {
+        float ms = 0.f;
+        double near_ms = 0.0, post_ms = 0.0;
+        for (int f = 0; f < nf; f++)
+            if (nq[f] > 0 &&
+                cudaEventElapsedTime(&ms, c->ev_near[2 * f], c->ev_near[2 * f + 1]) == cudaSuccess)
+                near_ms += ms;
+        if (cudaEventElapsedTime(&ms, c->ev1, c->ev_end) == cudaSuccess)
+            post_ms = ms;
+        std::lock_guard<std::mutex> lock(g_far_mu);
+        g_near_ms += near_ms;
+        g_post_ms += post_ms;
+    }
     for (int f = 0; f < nf; f++)
         if (h_cnt[8 + 8 * f + 4] != 0)
             return set_error(TVD_ERR_STACK_OVERFLOW, "Tesseroid stack overflow");

@@ -67,36 +67,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // ---------------------------------------------------------------------------------------------
-// FP64 building blocks
-// ---------------------------------------------------------------------------------------------
-// 1/sqrt(x) to ~1 ulp: MUFU.RSQ64H seed (>= 20 bits) + one third-order correction
-//   e = 1 - x*y0^2 ;  y = y0*(1 + e/2 + 3e^2/8)        (error ~ (5/16) e^3 < 2^-60)
-__device__ __forceinline__ double rsqrt_fast(double x)
-{
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    const double t = x * y0;
-    const double e = fma(-t, y0, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    const double q = e * p;
-    return fma(y0, q, y0);
-}
-
-// x^(-3/2) directly from the same seed (one operation fewer than cubing rsqrt_fast):
-//   e = 1 - x*y0^2 ;  x^(-3/2) = y0^3 (1 - e)^(-3/2) = y0^3 (1 + 3e/2 + 15e^2/8 + O(e^3))
-__device__ __forceinline__ double rsqrt3_fast(double x)
-{
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    const double s = y0 * y0;
-    const double e = fma(-x, s, 1.0);
-    const double c = s * y0;
-    const double p = fma(1.875, e, 1.5);
-    const double q = e * p;
-    return fma(c, q, c);
-}
-
-// ---------------------------------------------------------------------------------------------
 // cos / sincos of the longitude difference.
 //
 // libdevice's cos() costs ~20 FP64 + ~25 integer/branch/table-load instructions (special-case

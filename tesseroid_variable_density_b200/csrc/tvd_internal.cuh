@@ -141,6 +141,36 @@ __device__ __forceinline__ double tvd_cos(double x)
 }
 
 // ---------------------------------------------------------------------------------------------
+// FP64 building blocks
+// ---------------------------------------------------------------------------------------------
+// 1/sqrt(x) to ~1 ulp: MUFU.RSQ64H seed (>= 20 bits) + one third-order correction
+//   e = 1 - x*y0^2 ;  y = y0*(1 + e/2 + 3e^2/8)        (error ~ (5/16) e^3 < 2^-60)
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double t = x * y0;
+    const double e = fma(-t, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = e * p;
+    return fma(y0, q, y0);
+}
+
+// x^(-3/2) directly from the same seed (one operation fewer than cubing rsqrt_fast):
+//   e = 1 - x*y0^2 ;  x^(-3/2) = y0^3 (1 - e)^(-3/2) = y0^3 (1 + 3e/2 + 15e^2/8 + O(e^3))
+__device__ __forceinline__ double rsqrt3_fast(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double s = y0 * y0;
+    const double e = fma(-x, s, 1.0);
+    const double c = s * y0;
+    const double p = fma(1.875, e, 1.5);
+    const double q = e * p;
+    return fma(c, q, c);
+}
+
+// ---------------------------------------------------------------------------------------------
 // density-in-depth models (tvd_density_kind), evaluated in the reference scripts' own
 // operation order (no contraction: the TU is built with -fmad=false)
 // ---------------------------------------------------------------------------------------------
@@ -163,6 +193,7 @@ __device__ __forceinline__ double tvd_density(int kind, const double *__restrict
 // The same models with sin/exp evaluated in double-double and rounded once (tvd_ddmath.cuh):
 // used where the last bit decides discrete outcomes (K1) and where it is free (K4).
 #include "tvd_ddmath.cuh"
+#include "tvd_crtrig.cuh"
 __device__ __forceinline__ double tvd_density_cr(int kind, const double *__restrict__ p, double h)
 {
     switch (kind) {
@@ -265,9 +296,11 @@ struct NearArgs {
     double ratio;
     int stack_size;
     double *pair_result;             // [n_pairs]
-    unsigned long long *counters;    // nodes, leaves, splits, too_small, overflow flag
+    unsigned long long *counters;    // nodes, leaves, splits, too_small, overflow flag,
+                                     // root-leaf pairs, [6] = work counter (zeroed by the caller)
     int32_t *leaf_counts;            // NULL or [n_tess][n_points]
     int64_t n_points;
+    int batch;                       // pairs per work grab (set by the launcher)
 };
 cudaError_t tvd_launch_near(const NearArgs &a, cudaStream_t stream);
 // Phase C: result[p] = sum_g far[g][p] + sum of p's near-field pair results (key order)

@@ -1,95 +1,145 @@
 // tvd_near.cu -- Phase B (near-field pairs, literal adaptive subdivision) and Phase C (combine).
 //
 // Phase B restates rediscretizer (_tesseroid.pyx:34-98) for the (piece, point) pairs that the
-// far-field sweep could not prove to be far: one thread walks one pair depth-first in the
-// reference's own LIFO order with the literal distance_n_size / divisions / split /
-// scale_nodes / kernel arithmetic, so leaf sets (and hence subdivision counts) and the
-// per-pair summation order are the reference's.  The explicit stack holds one record per
-// subdivision LEVEL (parent w, s, dlon, dlat and the next child to visit) instead of one row per
-// pending node: children are regenerated with the reference's own expressions
-// w + i*dlon, w + (i+1)*dlon (:192-195) when they are popped, and the reference's row count
-// (`stktop`) is tracked separately to reproduce its overflow error (:88-89).
+// far-field sweep could not prove to be far.  Every node of the subdivision tree is tested with
+// the literal distance_n_size / divisions arithmetic (:104-146), its children are generated with
+// the reference's own expressions w + i*dlon, w + (i+1)*dlon (:187-195) and every leaf is
+// integrated with scale_nodes + kernel* (:152-176, :231-520), so leaf sets -- and hence
+// subdivision counts -- are the reference's.
 //
-// Pairs arrive sorted by (point, piece): neighbouring threads walk similar trees, and Phase C
-// adds a point's pair results in piece order, which makes every point's value independent of
-// how the points were sharded over blocks, groups or GPUs.
+// A WARP walks one pair at a time (north_star subsystem 2):
+//   * the pending nodes live in a per-warp double-ended queue in shared memory (4 doubles + one
+//     word per entry: top/bottom are invariant within a piece).  The queue only holds nodes that
+//     are already known to split; each step pops up to 8 of them, the 32 lanes generate and test
+//     their (up to 4) children, and warp votes compact the children that split again back into
+//     the queue and the leaves into a 64-entry leaf buffer;
+//   * nodes are taken from the FRONT (breadth-first: the frontier of these trees is a ring of
+//     ~4 pi D^2 cells per level, so two levels fit) and from the BACK (depth-first) when the
+//     queue runs short of room; a pair that still would not fit is redone depth-first one node
+//     at a time, which needs at most 3 entries per level;
+//   * whenever 32 leaves are buffered (or the tree is exhausted) the 32 lanes integrate one leaf
+//     each: leaf n of a pair is always summed by lane n mod 32 in increasing n, and the lanes
+//     are added by a fixed butterfly.  The traversal, and with it the summation order, is a
+//     function of the pair alone -- not of how pairs are batched, scheduled or sharded;
+//   * the reference's stack row index `stktop` after a node is popped is -1 + the sum of the
+//     push indices along its path, so each entry carries it and ValueError('Tesseroid stack
+//     overflow') (:88-89) is reproduced without replaying the reference's LIFO order;
+//   * the trigonometry is correctly rounded (tvd_crtrig.cuh: the values glibc returned to the
+//     reference), both for the split decisions and for the integration nodes.
+// Warps take batches of consecutive pairs from an atomic counter (the trees differ in size by
+// orders of magnitude); the roots of a batch are tested one per lane.
+//
+// Pairs arrive sorted by (point, piece); Phase C adds a point's pair results in piece order,
+// which makes every point's value independent of how the points were sharded over blocks, groups
+// or GPUs.
 #include "tvd_internal.cuh"
 
-// Near-field pairs are the worst-conditioned ones (cos psi and l^2 cancel hardest for the closest
-// cells), and there are few of them: the trigonometry of the integration nodes (scale_nodes and
-// cos(lon - lonc)) is evaluated in double-double and rounded once (tvd_ddmath.cuh), i.e. it
-// equals glibc's result wherever glibc rounds correctly.
+#define NW_CAP 512                  // queue entries per warp (power of two)
+#define NW_LEAFCAP 64               // leaf buffer entries per warp
+#define NW_WARPS 4                  // warps per block
+#define NW_FULL 0xffffffffu
 
-struct Level {
-    double w, s, dlon, dlat;
-    int nlon, nlat, next;
+struct NwWarp {                     // per-warp shared-memory state
+    double w[NW_CAP], e[NW_CAP], s[NW_CAP], n[NW_CAP];
+    // bit 0: splits in longitude, bit 1: splits in latitude, bits 2-7: depth,
+    // bits 8-: 1 + the reference's stktop after this node was popped
+    int meta[NW_CAP];
+    double lw[NW_LEAFCAP], le[NW_LEAFCAP], ls[NW_LEAFCAP], ln[NW_LEAFCAP];
 };
 
-struct NodeTrig {            // scale_nodes output (_tesseroid.pyx:152-176)
-    double lonc[2], sinlatc[2], coslatc[2], rc[2], scale;
+struct PairCtx {                    // what a (piece, point) pair contributes to every node
+    double lon, sinlat, coslat, radius, r_sqr;
+    double rt, rtop, dr;            // :111, :119, top - bottom
+    double rc[2], a2[2], b[2];      // radial nodes; 2*radius*rc[k]; r_sqr + rc[k]^2
+    double dkap[2];                 // density(rc[k] - R) * rc[k]^2   (or rc[k]^2: constant density)
+    double amp;                     // constant density: the density (:250), else 1
+    double ratio;
+    int stack_size;
 };
 
-__device__ __forceinline__ void scale_nodes(double w, double e, double s, double n, double top,
-                                            double bottom, NodeTrig &o)
+// distance_n_size + divisions (_tesseroid.pyx:104-146) of one cell: returns nlon-1 | (nlat-1) << 1
+// and counts the cell in `too_small` when it should split but is below the 0.1 m floor.
+__device__ __forceinline__ int node_test(const PairCtx &c, double w, double e, double s, double n,
+                                         int &too_small)
 {
-    const double dlon = e - w, dlat = n - s, dr = top - bottom;
+    const double lont = TVD_D2R * 0.5 * (w + e);
+    const double latt = TVD_D2R * 0.5 * (s + n);
+    double sinlatt, coslatt, sin_n, cos_n, sin_s, cos_s;
+    cr_sincos(latt, sinlatt, coslatt);
+    const double cospsi = c.sinlat * sinlatt + c.coslat * coslatt * cr_cos(c.lon - lont);
+    const double distance = sqrt(c.radius * c.radius + c.rt * c.rt - 2 * c.radius * c.rt * cospsi);
+    cr_sincos(TVD_D2R * n, sin_n, cos_n);
+    cr_sincos(TVD_D2R * s, sin_s, cos_s);
+    const double Llon = c.rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * cr_cos(TVD_D2R * (e - w)));
+    const double Llat = c.rtop * acos(sin_n * sin_s + cos_n * cos_s);
+    int code = 0;
+    const bool near_lon = distance <= c.ratio * Llon, near_lat = distance <= c.ratio * Llat;
+    // the reference overwrites error = -1, so a cell too small in both dimensions counts once
+    const bool small_lon = near_lon && Llon <= 0.1, small_lat = near_lat && Llat <= 0.1;
+    if (near_lon && !small_lon)
+        code |= 1;
+    if (near_lat && !small_lat)
+        code |= 2;
+    too_small += (small_lon || small_lat) ? 1 : 0;
+    return code;
+}
+
+// scale_nodes (_tesseroid.pyx:152-176) + kernel{V,x,y,z}[_variable] (:231-520) and the Fatiando 0.5
+// tensor integrands for one leaf cell.  cos psi and l^2 keep the reference's operation order;
+// l^-1 comes from the MUFU seed + one third-order correction instead of sqrt and a division.
+template <int FIELD>
+__device__ __forceinline__ double leaf_glq(const PairCtx &c, double w, double e, double s, double n)
+{
+    constexpr bool NEED_SIN = FIELD == TVD_GY || FIELD == TVD_GXY || FIELD == TVD_GYY ||
+                              FIELD == TVD_GYZ;
+    const double dlon = e - w, dlat = n - s;
     const double mlon = 0.5 * (e + w), mlat = 0.5 * (n + s);
-    const double mr = 0.5 * (top + bottom + 2. * TVD_R);
+    double coslon[2], sinlon[2], sinlatc[2], coslatc[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
-        o.lonc[i] = TVD_D2R * (0.5 * dlon * node + mlon);
+        const double lonc = TVD_D2R * (0.5 * dlon * node + mlon);
         const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
-        dd_sincos(latc, o.sinlatc[i], o.coslatc[i]);
-        o.rc[i] = (0.5 * dr * node + mr);
+        cr_sincos(latc, sinlatc[i], coslatc[i]);
+        if (NEED_SIN) {
+            // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
+            double sl;
+            cr_sincos(c.lon - lonc, sl, coslon[i]);
+            sinlon[i] = -sl;
+        } else {
+            coslon[i] = cr_cos(c.lon - lonc);
+            sinlon[i] = 0.0;
+        }
     }
-    o.scale = TVD_D2R * dlon * TVD_D2R * dlat * dr * 0.125;
-}
-
-// kernel{V,x,y,z}[_variable] (_tesseroid.pyx:231-520) and the Fatiando 0.5 tensor integrands.
-template <int FIELD>
-__device__ double glq_literal(bool variable, int kind, const double *p, double lon, double sinlat,
-                              double coslat, double radius, const NodeTrig &nd)
-{
-    const double r_sqr = radius * radius;
-    double dens[2] = {1.0, 1.0};
-    if (variable) {
-        dens[0] = tvd_density(kind, p, nd.rc[0] - TVD_R);
-        dens[1] = tvd_density(kind, p, nd.rc[1] - TVD_R);
-    }
+    const double scale = TVD_D2R * dlon * TVD_D2R * dlat * c.dr * 0.125;
     double result = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
-        double coslon, sinlon;
-        dd_sincos(lon - nd.lonc[i], sinlon, coslon);
-        sinlon = -sinlon;
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            const double kphi = coslat * nd.sinlatc[j] - sinlat * nd.coslatc[j] * coslon;
-            const double cospsi = sinlat * nd.sinlatc[j] + coslat * nd.coslatc[j] * coslon;
+            const double kphi = c.coslat * sinlatc[j] - c.sinlat * coslatc[j] * coslon[i];
+            const double cospsi = c.sinlat * sinlatc[j] + c.coslat * coslatc[j] * coslon[i];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                const double rc = nd.rc[k];
-                const double rc_sqr = rc * rc;
-                const double l_sqr = r_sqr + rc_sqr - 2 * radius * rc * cospsi;
-                const double kappa = rc_sqr * nd.coslatc[j];
-                const double dk = variable ? dens[k] * kappa : kappa;
-                const double l = sqrt(l_sqr);
+                const double rc = c.rc[k];
+                const double l_sqr = c.b[k] - c.a2[k] * cospsi;     // r^2 + rc^2 - 2 r rc cos psi
+                const double dk = c.dkap[k] * coslatc[j];           // [density *] kappa
+                const double y = rsqrt_fast(l_sqr);
                 double term;
                 if (FIELD == TVD_POTENTIAL) {
-                    term = dk / l;
+                    term = dk * y;
                 } else if (FIELD == TVD_GX) {
-                    term = dk * rc * kphi / (l_sqr * l);
+                    term = dk * rc * kphi * (y * y * y);
                 } else if (FIELD == TVD_GY) {
-                    term = dk * (rc * nd.coslatc[j] * sinlon / (l_sqr * l));
+                    term = dk * (rc * coslatc[j] * sinlon[i] * (y * y * y));
                 } else if (FIELD == TVD_GZ) {
-                    term = dk * (rc * cospsi - radius) / (l_sqr * l);
+                    term = dk * (rc * cospsi - c.radius) * (y * y * y);
                 } else {
                     const double dx = rc * kphi;
-                    const double dy = rc * nd.coslatc[j] * sinlon;
-                    const double dz = rc * cospsi - radius;
-                    const double l5 = l_sqr * l_sqr * l;
+                    const double dy = rc * coslatc[j] * sinlon[i];
+                    const double dz = rc * cospsi - c.radius;
+                    const double y2 = y * y;
+                    const double y5 = y2 * y2 * y;
                     double num;
                     if (FIELD == TVD_GXX) num = 3 * (dx * dx) - l_sqr;
                     else if (FIELD == TVD_GXY) num = 3 * dx * dy;
@@ -97,7 +147,7 @@ __device__ double glq_literal(bool variable, int kind, const double *p, double l
                     else if (FIELD == TVD_GYY) num = 3 * (dy * dy) - l_sqr;
                     else if (FIELD == TVD_GYZ) num = 3 * dy * dz;
                     else num = 3 * (dz * dz) - l_sqr;
-                    term = dk * num / l5;
+                    term = dk * num * y5;
                 }
                 result += term;
             }
@@ -105,154 +155,313 @@ __device__ double glq_literal(bool variable, int kind, const double *p, double l
     }
     if (FIELD == TVD_GZ)
         result *= -1;
-    if (variable)
-        return result * nd.scale;
-    return result * nd.scale * p[0];
+    return result * scale * c.amp;
+}
+
+// everything of a pair that does not depend on the cell
+__device__ __forceinline__ void make_pair_ctx(const NearArgs &a, int64_t pi, int64_t q, int64_t t,
+                                              PairCtx &c, double dens0, double dens1)
+{
+    c.lon = a.lon[pi];
+    c.sinlat = a.sinlat[pi];
+    c.coslat = a.coslat[pi];
+    c.radius = a.radius[pi];
+    c.r_sqr = c.radius * c.radius;
+    const double top = a.table.top[q], bottom = a.table.bottom[q];
+    c.rt = 0.5 * (top + bottom) + TVD_R;
+    c.rtop = top + TVD_R;
+    c.dr = top - bottom;
+    const double mr = 0.5 * (top + bottom + 2. * TVD_R);
+    const bool variable = a.table.tess_kind[t] != TVD_DENS_CONST;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double node = k == 0 ? -TVD_NODE : TVD_NODE;
+        c.rc[k] = (0.5 * c.dr * node + mr);
+        const double rc_sqr = c.rc[k] * c.rc[k];
+        c.a2[k] = 2 * c.radius * c.rc[k];
+        c.b[k] = c.r_sqr + rc_sqr;
+        // variable density: dens * kappa with kappa = rc_sqr * coslatc (:274-275); constant
+        // density: kappa alone, the density multiplies the sum (:250)
+        c.dkap[k] = variable ? (k == 0 ? dens0 : dens1) * rc_sqr : rc_sqr;
+    }
+    c.amp = variable ? 1.0 : a.table.tess_params[TVD_NPAR * t];
+    c.ratio = a.ratio;
+    c.stack_size = a.stack_size;
 }
 
 template <int FIELD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * NW_WARPS)
 near_walk(const NearArgs a)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_pairs)
-        return;
-    const unsigned long long key = a.keys[i];
-    const int64_t pi = (int64_t)(key >> 32);
-    const int64_t q = (int64_t)(key & 0xffffffffull);
-    const double lon = a.lon[pi], sinlat = a.sinlat[pi], coslat = a.coslat[pi], radius = a.radius[pi];
-    const int64_t t = a.table.parent[q];
-    const double top = a.table.top[q], bottom = a.table.bottom[q];
-    const int kind = a.table.tess_kind[t];
-    const bool variable = kind != TVD_DENS_CONST;
-    double p[TVD_NPAR];
-#pragma unroll
-    for (int k = 0; k < TVD_NPAR; k++)
-        p[k] = a.table.tess_params[TVD_NPAR * t + k];
-
-    Level stack[TVD_MAX_DEPTH];
-    int depth = 0;
-    int stktop = 0;                 // the reference's row index of the stack top (:73)
-    double w = a.table.tess_bounds[6 * t + 0], e = a.table.tess_bounds[6 * t + 1];
-    double s = a.table.tess_bounds[6 * t + 2], n = a.table.tess_bounds[6 * t + 3];
-    double res = 0.0;
-    unsigned long long nodes = 0, leaves = 0, splits = 0, too_small = 0;
+    extern __shared__ __align__(16) unsigned char nw_smem[];
+    NwWarp &S = reinterpret_cast<NwWarp *>(nw_smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // warp-uniform totals (every lane holds the same numbers)
+    unsigned long long t_nodes = 0, t_leaves = 0, t_splits = 0, t_small = 0, t_rootleaf = 0;
     bool overflow = false;
-    const double rt = 0.5 * (top + bottom) + TVD_R;       // :111, invariant within a piece
-    const double rtop = top + TVD_R;                      // :119
-    stktop -= 1;                                          // pop of the root (:81)
-    while (true) {
-        nodes++;
-        // distance_n_size (:104-123).  The split decision compares d with ratio*L where, for the
-        // small cells of a deep subdivision, L = rtop*acos(1 - tiny) is dominated by rounding: the
-        // reference's decision is then reproduced only by reproducing its roundings, i.e. with
-        // correctly rounded sin/cos (double-double, slow).  The geometry is therefore evaluated
-        // with the fast sin/cos first and accepted when the decision is safe against the
-        // difference between the two evaluations; otherwise it is redone in double-double.
-        double distance, Llon, Llat;
-        {
-            const double lont = TVD_D2R * 0.5 * (w + e);
-            const double latt = TVD_D2R * 0.5 * (s + n);
-            const double sinlatt = tvd_sin(latt), coslatt = tvd_cos(latt);
-            const double cospsi = sinlat * sinlatt + coslat * coslatt * tvd_cos(lon - lont);
-            const double d2 = radius * radius + rt * rt - 2 * radius * rt * cospsi;
-            distance = sqrt(d2);
-            const double arg_lon = sinlatt * sinlatt + (coslatt * coslatt) * tvd_cos(TVD_D2R * (e - w));
-            const double arg_lat = tvd_sin(TVD_D2R * n) * tvd_sin(TVD_D2R * s) +
-                                   tvd_cos(TVD_D2R * n) * tvd_cos(TVD_D2R * s);
-            Llon = rtop * acos(arg_lon);
-            Llat = rtop * acos(arg_lat);
-            // relative uncertainties: 1-ulp differences in the trig values move the acos arguments
-            // by ~2e-16 absolute (L ~ sqrt(2 (1 - arg))) and d^2 by ~2 r rt 2e-16 ~ 0.02 m^2
-            const double u_d = 0.02 / d2 + 1e-9;
-            const double u_lon = 4e-16 / (1.0 - arg_lon), u_lat = 4e-16 / (1.0 - arg_lat);
-            const double tl = a.ratio * Llon, tt = a.ratio * Llat;
-            const bool safe = fabs(distance - tl) > (u_d + u_lon) * tl &&
-                              fabs(distance - tt) > (u_d + u_lat) * tt;
-            if (!safe) {      // also taken for NaN / zero sizes (comparisons false)
-                double sl, cl, sn, cn, ss, cs;
-                dd_sincos(latt, sl, cl);
-                dd_sincos(TVD_D2R * n, sn, cn);
-                dd_sincos(TVD_D2R * s, ss, cs);
-                const double cp = sinlat * sl + coslat * cl * dd_cos(lon - lont);
-                distance = sqrt(radius * radius + rt * rt - 2 * radius * rt * cp);
-                Llon = rtop * acos(sl * sl + (cl * cl) * dd_cos(TVD_D2R * (e - w)));
-                Llat = rtop * acos(sn * ss + cn * cs);
-            }
-        }
-        // divisions (:129-146)
-        int nlon = 1, nlat = 1;
-        if (distance <= a.ratio * Llon) {
-            if (Llon <= 0.1)
-                too_small++;
-            else
-                nlon = 2;
-        }
-        if (distance <= a.ratio * Llat) {
-            if (Llat <= 0.1) {
-                // the reference overwrites error = -1 here, so a cell too small in both
-                // dimensions still counts once
-                if (!(distance <= a.ratio * Llon && Llon <= 0.1))
-                    too_small++;
-            } else {
-                nlat = 2;
-            }
-        }
-        const int new_cells = nlon * nlat;
-        if (new_cells > 1) {
-            if (stktop + new_cells > a.stack_size || depth >= TVD_MAX_DEPTH) {   // :88-89
-                overflow = true;
-                break;
-            }
-            splits++;
-            Level &L = stack[depth++];
-            L.w = w;
-            L.s = s;
-            L.dlon = (e - w) / nlon;                      // split (:187-188)
-            L.dlat = (n - s) / nlat;
-            L.nlon = nlon;
-            L.nlat = nlat;
-            L.next = new_cells - 1;
-            stktop += new_cells;
-        } else {
-            NodeTrig nd;
-            scale_nodes(w, e, s, n, top, bottom, nd);
-            res += glq_literal<FIELD>(variable, kind, p, lon, sinlat, coslat, radius, nd);
-            leaves++;
-        }
-        // pop the next pending node in LIFO order
-        while (depth > 0 && stack[depth - 1].next < 0)
-            depth--;
-        if (depth == 0)
+
+    for (;;) {
+        unsigned long long b = 0;
+        if (lane == 0)
+            b = atomicAdd(a.counters + 6, 1ull);
+        b = __shfl_sync(NW_FULL, b, 0);
+        const int64_t i0 = (int64_t)b * a.batch;
+        if (i0 >= a.n_pairs)
             break;
-        Level &L = stack[depth - 1];
-        const int c = L.next--;
-        stktop -= 1;
-        const int ci = c / L.nlat, cj = c - ci * L.nlat;
-        w = L.w + ci * L.dlon;                            // :192-195
-        e = L.w + (ci + 1) * L.dlon;
-        s = L.s + cj * L.dlat;
-        n = L.s + (cj + 1) * L.dlat;
+        const int nb = (int)((a.n_pairs - i0) < a.batch ? (a.n_pairs - i0) : a.batch);
+
+        // ---- roots of the batch, one per lane --------------------------------------------------
+        int root_code = 0, root_small = 0;
+        double dens0 = 0.0, dens1 = 0.0;
+        const bool have = lane < nb;
+        if (have) {
+            const unsigned long long key = a.keys[i0 + lane];
+            const int64_t pi = (int64_t)(key >> 32), q = (int64_t)(key & 0xffffffffull);
+            const int64_t t = a.table.parent[q];
+            const int kind = a.table.tess_kind[t];
+            if (kind != TVD_DENS_CONST) {
+                double p[TVD_NPAR];
+#pragma unroll
+                for (int k = 0; k < TVD_NPAR; k++)
+                    p[k] = a.table.tess_params[TVD_NPAR * t + k];
+                const double top = a.table.top[q], bottom = a.table.bottom[q];
+                const double mr = 0.5 * (top + bottom + 2. * TVD_R), hdr = 0.5 * (top - bottom);
+                dens0 = tvd_density(kind, p, (hdr * -TVD_NODE + mr) - TVD_R);    // :274
+                dens1 = tvd_density(kind, p, (hdr * TVD_NODE + mr) - TVD_R);
+            }
+            PairCtx c;
+            make_pair_ctx(a, pi, q, t, c, dens0, dens1);
+            const double w = a.table.tess_bounds[6 * t + 0], e = a.table.tess_bounds[6 * t + 1];
+            const double s = a.table.tess_bounds[6 * t + 2], n = a.table.tess_bounds[6 * t + 3];
+            root_code = node_test(c, w, e, s, n, root_small);
+            if (root_code == 0) {
+                // the conservative far test deferred a pair whose root is integrated after all
+                a.pair_result[i0 + lane] = leaf_glq<FIELD>(c, w, e, s, n);
+            } else if (-1 + (root_code == 3 ? 4 : 2) > c.stack_size) {
+                overflow = true;        // stktop + new_cells > STACK_SIZE at the root (:88)
+            }
+        }
+        {
+            const unsigned m_have = __ballot_sync(NW_FULL, have);
+            const unsigned m_leaf = __ballot_sync(NW_FULL, have && root_code == 0);
+            t_nodes += __popc(m_have);
+            t_leaves += __popc(m_leaf);
+            t_rootleaf += __popc(m_leaf);
+            t_small += __reduce_add_sync(NW_FULL, (unsigned)root_small);
+        }
+
+        // ---- the trees of the batch, one pair at a time -----------------------------------------
+        for (int jp = 0; jp < nb; jp++) {
+            const int rc0 = __shfl_sync(NW_FULL, root_code, jp);
+            const double d0 = __shfl_sync(NW_FULL, dens0, jp), d1 = __shfl_sync(NW_FULL, dens1, jp);
+            if (rc0 == 0)
+                continue;
+            const unsigned long long key = a.keys[i0 + jp];
+            const int64_t pi = (int64_t)(key >> 32), q = (int64_t)(key & 0xffffffffull);
+            const int64_t t = a.table.parent[q];
+            PairCtx c;
+            make_pair_ctx(a, pi, q, t, c, d0, d1);
+            unsigned p_nodes = 0, p_leaves = 0, p_splits = 0, p_small = 0;
+            double acc = 0.0;
+            // mode 0: breadth-first with depth-first relief; mode 1: depth-first, one node a step
+            for (int mode = 0; mode < 2; mode++) {
+                p_nodes = p_leaves = p_splits = p_small = 0;
+                acc = 0.0;
+                int head = 0, count = 1, nleaf = 0;
+                bool queue_full = false;
+                __syncwarp();
+                if (lane == 0) {
+                    S.w[0] = a.table.tess_bounds[6 * t + 0];
+                    S.e[0] = a.table.tess_bounds[6 * t + 1];
+                    S.s[0] = a.table.tess_bounds[6 * t + 2];
+                    S.n[0] = a.table.tess_bounds[6 * t + 3];
+                    S.meta[0] = rc0;                // depth 0, stktop after pop = -1
+                }
+                __syncwarp();
+                while (count > 0 || nleaf > 0) {
+                    if (count > 0) {
+                        const int room = NW_CAP - count;
+                        int k;
+                        bool from_back;
+                        if (mode == 1) {
+                            k = 1;
+                            from_back = true;
+                        } else if (room >= 64) {
+                            k = count < 8 ? count : 8;
+                            from_back = false;
+                        } else {
+                            k = count < 8 ? count : 8;
+                            if (k > room / 3)
+                                k = room / 3;
+                            from_back = true;
+                        }
+                        if (k == 0 || room < 3) {
+                            queue_full = true;
+                            break;
+                        }
+                        const int idx = lane >> 2, ch = lane & 3;
+                        bool valid = idx < k;
+                        double cw = 0, ce = 0, cs = 0, cn = 0;
+                        int cmeta = 0;
+                        if (valid) {
+                            const int pos = from_back ? ((head + count - 1 - idx) & (NW_CAP - 1))
+                                                      : ((head + idx) & (NW_CAP - 1));
+                            const double pw = S.w[pos], pe = S.e[pos], ps = S.s[pos], pn = S.n[pos];
+                            const int pm = S.meta[pos];
+                            const int nlon = 1 + (pm & 1), nlat = 1 + ((pm >> 1) & 1);
+                            valid = ch < nlon * nlat;
+                            // split (:187-195): children in push order (i, j) = (0,0),(0,1),(1,0),(1,1)
+                            const int ci = nlat == 2 ? (ch >> 1) : ch, cj = ch - ci * nlat;
+                            const double dlon = (pe - pw) / nlon, dlat = (pn - ps) / nlat;
+                            cw = pw + ci * dlon;
+                            ce = pw + (ci + 1) * dlon;
+                            cs = ps + cj * dlat;
+                            cn = ps + (cj + 1) * dlat;
+                            // a child pushed with index ch is popped with ch siblings still below it
+                            cmeta = ((((pm >> 2) & 63) + 1) << 2) | (((pm >> 8) + ch) << 8);
+                        }
+                        __syncwarp();       // every parent is in registers before slots are reused
+                        if (!from_back)
+                            head = (head + k) & (NW_CAP - 1);
+                        count -= k;
+                        int code = 0, small = 0;
+                        if (valid)
+                            code = node_test(c, cw, ce, cs, cn, small);
+                        const bool split = valid && code != 0;
+                        const bool leaf = valid && code == 0;
+                        if (split) {
+                            const int stk = (cmeta >> 8) - 1, cells = code == 3 ? 4 : 2;
+                            if (stk + cells > c.stack_size || ((cmeta >> 2) & 63) >= TVD_MAX_DEPTH - 1)
+                                overflow = true;                        // :88-89
+                        }
+                        const unsigned m_valid = __ballot_sync(NW_FULL, valid);
+                        const unsigned m_split = __ballot_sync(NW_FULL, split);
+                        const unsigned m_leaf = __ballot_sync(NW_FULL, leaf);
+                        p_nodes += __popc(m_valid);
+                        p_splits += __popc(m_split);
+                        p_leaves += __popc(m_leaf);
+                        p_small += __reduce_add_sync(NW_FULL, (unsigned)small);
+                        if (split) {
+                            const int pos = (head + count + __popc(m_split & lt_mask)) & (NW_CAP - 1);
+                            S.w[pos] = cw;
+                            S.e[pos] = ce;
+                            S.s[pos] = cs;
+                            S.n[pos] = cn;
+                            S.meta[pos] = cmeta | code;
+                        }
+                        if (leaf) {
+                            const int pos = nleaf + __popc(m_leaf & lt_mask);
+                            S.lw[pos] = cw;
+                            S.le[pos] = ce;
+                            S.ls[pos] = cs;
+                            S.ln[pos] = cn;
+                        }
+                        count += __popc(m_split);
+                        nleaf += __popc(m_leaf);
+                        __syncwarp();
+                        if (__any_sync(NW_FULL, overflow)) {
+                            overflow = true;
+                            break;
+                        }
+                    }
+                    if (nleaf >= 32 || (count == 0 && nleaf > 0)) {
+                        const int m = nleaf < 32 ? nleaf : 32;
+                        if (lane < m)
+                            acc += leaf_glq<FIELD>(c, S.lw[lane], S.le[lane], S.ls[lane], S.ln[lane]);
+                        __syncwarp();
+                        const int rest = nleaf - m;         // < 32: no overlap with the slots read
+                        double mw = 0, me = 0, ms = 0, mn = 0;
+                        if (lane < rest) {
+                            mw = S.lw[32 + lane];
+                            me = S.le[32 + lane];
+                            ms = S.ls[32 + lane];
+                            mn = S.ln[32 + lane];
+                        }
+                        __syncwarp();
+                        if (lane < rest) {
+                            S.lw[lane] = mw;
+                            S.le[lane] = me;
+                            S.ls[lane] = ms;
+                            S.ln[lane] = mn;
+                        }
+                        nleaf = rest;
+                        __syncwarp();
+                    }
+                }
+                if (!queue_full || overflow)
+                    break;
+                if (mode == 1)
+                    overflow = true;    // unreachable: depth-first needs <= 3 entries per level
+            }
+            // fixed butterfly: every lane ends with the same bits
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc += __shfl_xor_sync(NW_FULL, acc, o);
+            if (lane == 0) {
+                a.pair_result[i0 + jp] = acc;
+                if (a.leaf_counts)
+                    atomicAdd(&a.leaf_counts[t * a.n_points + pi], (int)p_leaves - 1);
+            }
+            t_nodes += p_nodes;
+            t_leaves += p_leaves;
+            t_splits += p_splits + 1;       // + the root
+            t_small += p_small;
+            if (overflow)
+                break;
+        }
+        if (__any_sync(NW_FULL, overflow)) {
+            overflow = true;
+            break;
+        }
     }
-    a.pair_result[i] = res;
-    atomicAdd(&a.counters[0], nodes);
-    atomicAdd(&a.counters[1], leaves);
-    atomicAdd(&a.counters[2], splits);
-    atomicAdd(&a.counters[3], too_small);
-    if (overflow)
-        atomicExch(&a.counters[4], 1ull);
-    if (splits == 0)
-        atomicAdd(&a.counters[5], 1ull);   // pairs whose root was integrated after all
-    if (a.leaf_counts)
-        atomicAdd(&a.leaf_counts[t * a.n_points + pi], (int)leaves - 1);
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], t_nodes);
+        atomicAdd(&a.counters[1], t_leaves);
+        atomicAdd(&a.counters[2], t_splits);
+        atomicAdd(&a.counters[3], t_small);
+        if (overflow)
+            atomicExch(&a.counters[4], 1ull);
+        atomicAdd(&a.counters[5], t_rootleaf);
+    }
 }
 
 template <int FIELD>
-static cudaError_t launch_near_field(const NearArgs &a, cudaStream_t stream)
+static cudaError_t launch_near_field(NearArgs a, cudaStream_t stream)
 {
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((a.n_pairs + threads - 1) / threads);
-    near_walk<FIELD><<<blocks, threads, 0, stream>>>(a);
+    static int blocks_per_sm[64] = {0};
+    const size_t smem = sizeof(NwWarp) * NW_WARPS;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return e;
+    if (dev < 0 || dev >= 64)
+        return cudaErrorInvalidDevice;
+    if (blocks_per_sm[dev] == 0) {
+        e = cudaFuncSetAttribute(near_walk<FIELD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+        if (e != cudaSuccess)
+            return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, near_walk<FIELD>, 32 * NW_WARPS, smem);
+        if (e != cudaSuccess)
+            return e;
+        blocks_per_sm[dev] = nb > 0 ? nb : 1;
+    }
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess)
+        return e;
+    const int64_t warps = (int64_t)sms * blocks_per_sm[dev] * NW_WARPS;
+    // batches of consecutive pairs per grab: 32 when there is plenty of work, fewer when the pairs
+    // would not keep every warp busy (the results do not depend on it)
+    int64_t batch = a.n_pairs / (4 * warps);
+    batch = batch < 1 ? 1 : (batch > 32 ? 32 : batch);
+    a.batch = (int)batch;
+    const int64_t n_batches = (a.n_pairs + batch - 1) / batch;
+    int64_t blocks = (n_batches + NW_WARPS - 1) / NW_WARPS;
+    if (blocks > (int64_t)sms * blocks_per_sm[dev])
+        blocks = (int64_t)sms * blocks_per_sm[dev];
+    near_walk<FIELD><<<(unsigned)blocks, 32 * NW_WARPS, smem, stream>>>(a);
     tvd_count_launch();
     return cudaGetLastError();
 }

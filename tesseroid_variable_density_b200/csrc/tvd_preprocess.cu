@@ -587,7 +587,17 @@ __global__ void debug_math_kernel(int func, int64_t n, const double *__restrict_
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    out[i] = func == 0 ? dd_sin(x[i]) : func == 1 ? dd_cos(x[i]) : dd_exp(x[i]);
+    double v;
+    switch (func) {
+    case 0: v = dd_sin(x[i]); break;
+    case 1: v = dd_cos(x[i]); break;
+    case 2: v = dd_exp(x[i]); break;
+    case 3: v = cr_sin(x[i]); break;          // table-based correctly rounded (tvd_crtrig.cuh)
+    case 4: v = cr_cos(x[i]); break;
+    case 5: { double c; cr_sincos(x[i], v, c); break; }
+    default: { double s; cr_sincos(x[i], s, v); break; }
+    }
+    out[i] = v;
 }
 
 cudaError_t tvd_debug_math_launch(int func, int64_t n, const double *d_x, double *d_out,

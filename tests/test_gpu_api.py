@@ -202,6 +202,38 @@ def test_double_double_math_is_correctly_rounded():
         assert np.mean(out == glibc) >= 0.99
 
 
+def test_table_trig_equals_double_double():
+    """The near-field walk's sin/cos (tvd_crtrig.cuh: table + Ziv's rounding test, double-double
+    only when the test fails) must return the bits of the double-double versions, i.e. the
+    correctly rounded values -- what glibc handed the reference."""
+    import mpmath
+    mpmath.mp.dps = 60
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-0.8, 0.8, 400000), rng.uniform(-1.6, 1.6, 400000),
+                        rng.uniform(-7, 7, 400000), rng.uniform(-400, 400, 200000),
+                        rng.uniform(-1e-3, 1e-3, 100000), rng.uniform(-1e-9, 1e-9, 1000),
+                        np.array([0.0, -0.0, 1e-300, np.pi / 4, -np.pi / 4, np.pi / 2, np.pi,
+                                  0.78539816339744828, 0.78539816339744839, 1e5, 9.9e5, 1e7,
+                                  np.inf, np.nan])])
+    x = np.ascontiguousarray(x)
+
+    def run(func):
+        out = np.empty_like(x)
+        assert lib.tvd_debug_math(0, func, x.size, _lib.ptr_f64(x), _lib.ptr_f64(out)) == 0
+        return out
+    dd_s, dd_c = run(0), run(1)
+    for func, want in ((3, dd_s), (4, dd_c), (5, dd_s), (6, dd_c)):
+        got = run(func)
+        same = (got == want) | (np.isnan(got) & np.isnan(want))
+        assert np.all(same), (func, int(np.sum(~same)), x[~same][:5])
+    assert np.signbit(run(3)[x.size - 13])            # sin(-0.0) = -0.0
+    idx = rng.choice(1500000, 3000, replace=False)
+    ms = np.array([float(mpmath.sin(mpmath.mpf(float(v)))) for v in x[idx]])
+    mc = np.array([float(mpmath.cos(mpmath.mpf(float(v)))) for v in x[idx]])
+    assert np.array_equal(run(3)[idx], ms) and np.array_equal(run(4)[idx], mc)
+
+
 def test_k1_tie_breaking_with_whole_periods(oracle_lib):
     """A sine with a whole number of periods over the tesseroid has mathematically equal maxima
     of |rho_n - line|; the split list is then decided by the last bit of sin()."""
