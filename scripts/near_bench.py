@@ -69,6 +69,21 @@ def main():
     lib = _lib.load()
     out = []
     mesh = cases.exponential_case(1e3, 30)[0]
+    # model set-up latency (flattening + K1 + tables) for the 72-tesseroid shell
+    from tesseroid_variable_density_b200.model import flatten_model
+    flat = flatten_model(mesh)
+    PreparedModel(flat, delta=0.1).close()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        PreparedModel(flat, delta=0.1).close()
+    t_model = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        PreparedModel(mesh, delta=0.1).close()
+    t_model_flat = (time.perf_counter() - t0) / 20
+    print("PreparedModel(72 tesseroids, exp density, delta=0.1): %.3f ms from a FlatModel, %.3f ms "
+          "from the mesh object" % (t_model * 1e3, t_model_flat * 1e3), flush=True)
+    out.append({"case": "model_setup_72", "ms_flat": t_model * 1e3, "ms_mesh": t_model_flat * 1e3})
     lats, lons, heights = cases.GRIDS["global2km"]()
     cc = _convert_coords(lons, lats, heights)
     pm = PreparedModel(mesh, delta=0.1)

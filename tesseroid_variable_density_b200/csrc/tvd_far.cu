@@ -77,7 +77,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // i.e. it agrees with glibc's cos, which the reference calls).  When every lane of the warp
 // has |x| <= pi/4 (regional models) no reduction is done at all.
 // ---------------------------------------------------------------------------------------------
-// cos (and, if WANT_SIN, sin) of two arguments.  Warp-uniform fast path for |x| <= pi/4.
+// cos (and, if WANT_SIN, sin) of two arguments.  Every lane's result is a function of its own
+// argument alone: the warp votes below only choose between code paths that return the same bits
+// (a point's value must not depend on which points share its warp, i.e. on how the points were
+// chunked over devices or ranks).
+//   * |x| < pi/4 for the whole warp: the reduction is skipped; it would return k = 0, r = x and a
+//     zero tail, so kcos(x, 0) / ksin(x, 0) ARE the general path's values;
+//   * huge, infinite or NaN arguments: libdevice, decided per lane after the common path.
 template <bool WANT_SIN>
 __device__ __forceinline__ void trig2(double x0, double x1, double &c0, double &c1, double &s0,
                                       double &s1)
@@ -87,22 +93,11 @@ __device__ __forceinline__ void trig2(double x0, double x1, double &c0, double &
     const bool small = ((__double2hiint(x0) & 0x7fffffff) < 0x3fe921fb) &&
                        ((__double2hiint(x1) & 0x7fffffff) < 0x3fe921fb);
     if (__all_sync(0xffffffffu, small)) {
-        c0 = kcos0(x0);
-        c1 = kcos0(x1);
+        c0 = kcos(x0, 0.0);
+        c1 = kcos(x1, 0.0);
         if (WANT_SIN) {
-            s0 = ksin0(x0);
-            s1 = ksin0(x1);
-        }
-        return;
-    }
-    const bool huge = !(fmax(fabs(x0), fabs(x1)) < 1.0e5);      // also catches NaN/inf
-    if (__any_sync(0xffffffffu, huge)) {
-        if (WANT_SIN) {
-            sincos(x0, &s0, &c0);
-            sincos(x1, &s1, &c1);
-        } else {
-            c0 = cos(x0);
-            c1 = cos(x1);
+            s0 = ksin(x0, 0.0);
+            s1 = ksin(x1, 0.0);
         }
         return;
     }
@@ -125,6 +120,19 @@ __device__ __forceinline__ void trig2(double x0, double x1, double &c0, double &
             c1 = c;
             s1 = sn;
         }
+    }
+    // the Cody-Waite reduction is only valid for moderate arguments
+    if (!(fabs(x0) < 1.0e5)) {      // also catches NaN/inf
+        if (WANT_SIN)
+            sincos(x0, &s0, &c0);
+        else
+            c0 = cos(x0);
+    }
+    if (!(fabs(x1) < 1.0e5)) {
+        if (WANT_SIN)
+            sincos(x1, &s1, &c1);
+        else
+            c1 = cos(x1);
     }
 }
 
@@ -469,7 +477,7 @@ far_sweep(const FarArgs a)
         // votes or predicated accumulation.  The far sums are the same either way.
         bool tile_far = true;
         {
-            const double *tr = a.tile_rec + ((q0 / TVD_TILE) * TVD_TILE_REC);
+            const double *tr = a.tile_rec + ((int64_t)g * a.tiles_per_group + tile) * TVD_TILE_REC;
             double tc = fma(pt.p2x, __ldg(tr + 0), __ldg(tr + 3));
             tc = fma(pt.p2y, __ldg(tr + 1), tc);
             tc = fma(pt.p2z, __ldg(tr + 2), tc);

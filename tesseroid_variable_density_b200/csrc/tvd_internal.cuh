@@ -206,7 +206,7 @@ __device__ __forceinline__ double tvd_density_cr(int kind, const double *__restr
     case TVD_DENS_EXP:
         return p[0] * dd_exp(p[1] * (h - p[2]) / p[3]) + p[4];
     default:
-        return p[0] * dd_sin(p[1] * h) + p[2];
+        return p[0] * cr_sin(p[1] * h) + p[2];      // same bits as dd_sin (tvd_crtrig.cuh)
     }
 }
 
@@ -227,25 +227,35 @@ struct PieceTable {
 
 // ---- launchers implemented in the .cu files (all asynchronous on `stream`) -------------------
 // K1: density-based radial discretisation.  counts pass then emit pass.
+// d_keep: scratch [n_tess][TVD_K1_KEEP][2], pieces of tesseroids with few pieces handed from the
+// count pass to the emit pass
+#define TVD_K1_KEEP 8
 cudaError_t tvd_launch_k1_count(const PieceTable &t, double delta, int has_delta, int *d_status,
-                                cudaStream_t stream);
+                                double *d_keep, cudaStream_t stream);
 cudaError_t tvd_launch_scan(const int32_t *d_counts, int64_t *d_offsets, int64_t n,
                             cudaStream_t stream);   // exclusive scan, d_offsets[n] = total
 cudaError_t tvd_launch_k1_emit(const PieceTable &t, const int64_t *d_offsets, double delta,
-                               int has_delta, cudaStream_t stream);
+                               int has_delta, double *d_keep, cudaStream_t stream);
 // K4: per-piece root records for the far-field sweep.  The GLQ records depend on the model
 // only; the test records on the distance-size ratio of each field of the sweep.
-cudaError_t tvd_launch_pack_glq(const PieceTable &t, double *d_glq, double *d_geom,
+// `period`: the "same tesseroid / same longitude extent" flags of the GLQ records are reset at
+// every multiple of it (groups and tiles of the sweep start there)
+cudaError_t tvd_launch_pack_glq(const PieceTable &t, int period, double *d_glq, double *d_geom,
                                 cudaStream_t stream);
 struct RatioList {
     int nf;
     double ratio[TVD_MAX_FUSED];
 };
 cudaError_t tvd_launch_pack_test(const PieceTable &t, const double *d_geom, RatioList ratios,
-                                 double *d_test, double *d_tile, cudaStream_t stream);
+                                 double *d_test, cudaStream_t stream);
 // per-tile record of the sweep: Cx Cy Cz |C|^2 lim_0 .. lim_5 (bounding sphere of the tile's piece
-// centres; a point farther than sqrt(lim_f) from C is far from every piece of the tile for field f)
+// centres; a point farther than sqrt(lim_f) from C is far from every piece of the tile for field f).
+// Tiles are those of the sweep's grouping: tile k of group g covers the pieces
+// [g*ppg + k*TVD_TILE, ...) and its record is number g*ceil(ppg/TVD_TILE) + k.
 #define TVD_TILE_REC 10
+cudaError_t tvd_launch_pack_tiles(const PieceTable &t, const double *d_geom, RatioList ratios,
+                                  int64_t pieces_per_group, int n_groups, double *d_tile,
+                                  cudaStream_t stream);
 // points-at-one-height specialisation: per piece 2r*rc0 2r*rc1 r^2+rc0^2 r^2+rc1^2 (sweep order)
 #define TVD_AB_REC 4
 cudaError_t tvd_launch_pack_ab(const PieceTable &t, const double *d_glq, double radius,
@@ -264,6 +274,7 @@ struct FarArgs {
     const double *ab_rec;            // non-NULL: all points share one radius (see TVD_AB_REC)
     int n_groups;
     int64_t pieces_per_group;
+    int tiles_per_group;             // ceil(pieces_per_group / TVD_TILE)
     double *far_out;                 // [nf][n_groups][n_points]
     unsigned long long *queue;       // [nf][qcap] near-field pairs: (point << 32) | piece
     unsigned long long *qcount;      // [nf]
@@ -301,7 +312,13 @@ struct NearArgs {
     int32_t *leaf_counts;            // NULL or [n_tess][n_points]
     int64_t n_points;
     int batch;                       // pairs per work grab (set by the launcher)
+    void *workspace;                 // tvd_near_workspace_bytes(n_pairs) bytes
+    // carved out of the workspace by the launcher
+    unsigned char *root_code, *root_class;
+    int32_t *order;
+    unsigned *bins;
 };
+size_t tvd_near_workspace_bytes(int64_t n_pairs);
 cudaError_t tvd_launch_near(const NearArgs &a, cudaStream_t stream);
 // Phase C: result[p] = sum_g far[g][p] + sum of p's near-field pair results (key order)
 cudaError_t tvd_launch_combine(int64_t n_points, int n_groups, const double *far_out,

@@ -34,11 +34,35 @@
 // or GPUs.
 #include "tvd_internal.cuh"
 
-#define NW_CAP 512                  // queue entries per warp (power of two)
+// queue entries per warp (powers of two): the breadth-first frontier holds ~2 x pi D^2 splitting
+// cells, so 256 entries serve the default ratios of the potential and gx, gy, gz (D <= 2.5) with
+// twice the resident warps, and 512 the tensor's D = 8; larger ratios fall back on depth-first
+// steps (slower, never wrong)
+#define NW_CAP_SMALL 256
+#define NW_CAP_LARGE 512
+#define NW_RATIO_SMALL 3.2          // largest ratio served by the small queue
 #define NW_LEAFCAP 64               // leaf buffer entries per warp
+#ifndef NW_WARPS
 #define NW_WARPS 4                  // warps per block
+#endif
 #define NW_FULL 0xffffffffu
+// The walk calls sin/cos from nine places; out of line the kernel is a third of the size, which
+// matters because few warps are resident (instruction fetch stalls were the top stall reason
+// with the inlined form, profiles/near_walk_r2.md).
+#ifndef NW_INLINE_TRIG
+#define NW_SINCOS(ARG_, S_, C_)                    \
+    do {                                           \
+        const double2 _r = cr_sincos_call(ARG_);   \
+        S_ = _r.x;                                 \
+        C_ = _r.y;                                 \
+    } while (0)
+#define NW_COS(ARG_) cr_cos_call(ARG_)
+#else
+#define NW_SINCOS(ARG_, S_, C_) cr_sincos(ARG_, S_, C_)
+#define NW_COS(ARG_) cr_cos(ARG_)
+#endif
 
+template <int NW_CAP>
 struct NwWarp {                     // per-warp shared-memory state
     double w[NW_CAP], e[NW_CAP], s[NW_CAP], n[NW_CAP];
     // bit 0: splits in longitude, bit 1: splits in latitude, bits 2-7: depth,
@@ -57,31 +81,50 @@ struct PairCtx {                    // what a (piece, point) pair contributes to
     int stack_size;
 };
 
-// distance_n_size + divisions (_tesseroid.pyx:104-146) of one cell: returns nlon-1 | (nlat-1) << 1
-// and counts the cell in `too_small` when it should split but is below the 0.1 m floor.
-__device__ __forceinline__ int node_test(const PairCtx &c, double w, double e, double s, double n,
-                                         int &too_small)
+// distance_n_size + divisions (_tesseroid.pyx:104-146) of one cell: returns nlon-1 | (nlat-1) << 1,
+// and bit 2 when the cell should split but is below the 0.1 m floor (the reference's error
+// count).  Out of line: it is called for the roots and inside the walk.
+struct NodeTest {
+    int code;       // nlon-1 | (nlat-1) << 1 | too-small << 2
+    float key;      // ratio * max(Llon, Llat) / distance: >= 1 for a cell that splits, and the
+                    // larger the deeper its subtree (an estimate, used for scheduling only)
+};
+static __device__ __noinline__ NodeTest node_test_call(double w, double e, double s, double n,
+                                                       double lon, double sinlat, double coslat,
+                                                       double radius, double rt, double rtop,
+                                                       double ratio)
 {
     const double lont = TVD_D2R * 0.5 * (w + e);
     const double latt = TVD_D2R * 0.5 * (s + n);
     double sinlatt, coslatt, sin_n, cos_n, sin_s, cos_s;
-    cr_sincos(latt, sinlatt, coslatt);
-    const double cospsi = c.sinlat * sinlatt + c.coslat * coslatt * cr_cos(c.lon - lont);
-    const double distance = sqrt(c.radius * c.radius + c.rt * c.rt - 2 * c.radius * c.rt * cospsi);
-    cr_sincos(TVD_D2R * n, sin_n, cos_n);
-    cr_sincos(TVD_D2R * s, sin_s, cos_s);
-    const double Llon = c.rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * cr_cos(TVD_D2R * (e - w)));
-    const double Llat = c.rtop * acos(sin_n * sin_s + cos_n * cos_s);
-    int code = 0;
-    const bool near_lon = distance <= c.ratio * Llon, near_lat = distance <= c.ratio * Llat;
+    NW_SINCOS(latt, sinlatt, coslatt);
+    const double cospsi = sinlat * sinlatt + coslat * coslatt * NW_COS(lon - lont);
+    const double distance = sqrt(radius * radius + rt * rt - 2 * radius * rt * cospsi);
+    NW_SINCOS(TVD_D2R * n, sin_n, cos_n);
+    NW_SINCOS(TVD_D2R * s, sin_s, cos_s);
+    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * NW_COS(TVD_D2R * (e - w)));
+    const double Llat = rtop * acos(sin_n * sin_s + cos_n * cos_s);
+    NodeTest r;
+    r.code = 0;
+    const bool near_lon = distance <= ratio * Llon, near_lat = distance <= ratio * Llat;
     // the reference overwrites error = -1, so a cell too small in both dimensions counts once
     const bool small_lon = near_lon && Llon <= 0.1, small_lat = near_lat && Llat <= 0.1;
     if (near_lon && !small_lon)
-        code |= 1;
+        r.code |= 1;
     if (near_lat && !small_lat)
-        code |= 2;
-    too_small += (small_lon || small_lat) ? 1 : 0;
-    return code;
+        r.code |= 2;
+    if (small_lon || small_lat)
+        r.code |= 4;
+    r.key = (float)(ratio * fmax(Llon, Llat)) / (float)distance;
+    return r;
+}
+__device__ __forceinline__ int node_test(const PairCtx &c, double w, double e, double s, double n,
+                                         int &too_small)
+{
+    const NodeTest r = node_test_call(w, e, s, n, c.lon, c.sinlat, c.coslat, c.radius, c.rt,
+                                      c.rtop, c.ratio);
+    too_small += (r.code >> 2) & 1;
+    return r.code & 3;
 }
 
 // scale_nodes (_tesseroid.pyx:152-176) + kernel{V,x,y,z}[_variable] (:231-520) and the Fatiando 0.5
@@ -100,14 +143,14 @@ __device__ __forceinline__ double leaf_glq(const PairCtx &c, double w, double e,
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
         const double lonc = TVD_D2R * (0.5 * dlon * node + mlon);
         const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
-        cr_sincos(latc, sinlatc[i], coslatc[i]);
+        NW_SINCOS(latc, sinlatc[i], coslatc[i]);
         if (NEED_SIN) {
             // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
             double sl;
-            cr_sincos(c.lon - lonc, sl, coslon[i]);
+            NW_SINCOS(c.lon - lonc, sl, coslon[i]);
             sinlon[i] = -sl;
         } else {
-            coslon[i] = cr_cos(c.lon - lonc);
+            coslon[i] = NW_COS(c.lon - lonc);
             sinlon[i] = 0.0;
         }
     }
@@ -189,17 +232,117 @@ __device__ __forceinline__ void make_pair_ctx(const NearArgs &a, int64_t pi, int
     c.stack_size = a.stack_size;
 }
 
+// densities at the two radial GLQ nodes of a piece (:274), 1 for a constant density
+__device__ __forceinline__ void pair_densities(const NearArgs &a, int64_t q, int64_t t,
+                                               double &dens0, double &dens1)
+{
+    dens0 = dens1 = 1.0;
+    const int kind = a.table.tess_kind[t];
+    if (kind == TVD_DENS_CONST)
+        return;
+    double p[TVD_NPAR];
+#pragma unroll
+    for (int k = 0; k < TVD_NPAR; k++)
+        p[k] = a.table.tess_params[TVD_NPAR * t + k];
+    const double top = a.table.top[q], bottom = a.table.bottom[q];
+    const double mr = 0.5 * (top + bottom + 2. * TVD_R), hdr = 0.5 * (top - bottom);
+    dens0 = tvd_density(kind, p, (hdr * -TVD_NODE + mr) - TVD_R);
+    dens1 = tvd_density(kind, p, (hdr * TVD_NODE + mr) - TVD_R);
+}
+
+// Roots, one THREAD per pair: the literal test of the root cell.  A root that does not split
+// after all (the sweep's far test is conservative) is integrated here; the others are filed by
+// the estimated depth of their tree (class = exponent of ratio*L/d), so that the walk can start
+// with the deepest trees -- they are orders of magnitude longer than the median and would
+// otherwise finish alone at the end.
+//   ws layout: code[n] (uint8: split code, 0 = done), klass[n] (uint8), order[n] (int32),
+//   bins[64] (uint32: [0..31] pairs per class, [32..63] scatter cursors)
 template <int FIELD>
+__global__ void __launch_bounds__(128)
+near_roots(const NearArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = i < a.n_pairs;
+    int code = 0, small = 0, klass = 255;
+    bool overflow = false;
+    if (have) {
+        const unsigned long long key = a.keys[i];
+        const int64_t pi = (int64_t)(key >> 32), q = (int64_t)(key & 0xffffffffull);
+        const int64_t t = a.table.parent[q];
+        double dens0, dens1;
+        pair_densities(a, q, t, dens0, dens1);
+        PairCtx c;
+        make_pair_ctx(a, pi, q, t, c, dens0, dens1);
+        const double w = a.table.tess_bounds[6 * t + 0], e = a.table.tess_bounds[6 * t + 1];
+        const double s = a.table.tess_bounds[6 * t + 2], n = a.table.tess_bounds[6 * t + 3];
+        const NodeTest r = node_test_call(w, e, s, n, c.lon, c.sinlat, c.coslat, c.radius, c.rt,
+                                          c.rtop, c.ratio);
+        code = r.code & 3;
+        small = (r.code >> 2) & 1;
+        if (code == 0) {
+            a.pair_result[i] = leaf_glq<FIELD>(c, w, e, s, n);
+        } else {
+            if (-1 + (code == 3 ? 4 : 2) > c.stack_size)
+                overflow = true;        // stktop + new_cells > STACK_SIZE at the root (:88)
+            int ex = 0;
+            frexpf(r.key, &ex);         // key in [2^(ex-1), 2^ex)
+            klass = ex < 0 ? 0 : (ex > 31 ? 31 : ex);
+            atomicAdd(a.bins + klass, 1u);
+        }
+        a.root_code[i] = (unsigned char)code;
+        a.root_class[i] = (unsigned char)klass;
+    }
+    const unsigned m_have = __ballot_sync(NW_FULL, have);
+    const unsigned m_leaf = __ballot_sync(NW_FULL, have && code == 0);
+    const unsigned n_small = __reduce_add_sync(NW_FULL, (unsigned)small);
+    const bool any_over = __any_sync(NW_FULL, overflow);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&a.counters[0], (unsigned long long)__popc(m_have));
+        if (m_leaf) {
+            atomicAdd(&a.counters[1], (unsigned long long)__popc(m_leaf));
+            atomicAdd(&a.counters[5], (unsigned long long)__popc(m_leaf));
+        }
+        if (n_small)
+            atomicAdd(&a.counters[3], (unsigned long long)n_small);
+        if (any_over)
+            atomicExch(&a.counters[4], 1ull);
+    }
+}
+
+// order[] = the pairs that split, deepest class first (any order within a class: a pair's value
+// does not depend on when it is walked)
+__global__ void __launch_bounds__(256)
+near_order(const NearArgs a)
+{
+    __shared__ unsigned start[32];
+    if (threadIdx.x < 32) {
+        unsigned s = 0;
+        for (int k = 31; k > (int)threadIdx.x; k--)
+            s += a.bins[k];
+        start[threadIdx.x] = s;
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_pairs)
+        return;
+    const int k = a.root_class[i];
+    if (k > 31)
+        return;
+    a.order[start[k] + atomicAdd(a.bins + 32 + k, 1u)] = (int32_t)i;
+}
+
+template <int FIELD, int NW_CAP>
 __global__ void __launch_bounds__(32 * NW_WARPS)
 near_walk(const NearArgs a)
 {
     extern __shared__ __align__(16) unsigned char nw_smem[];
-    NwWarp &S = reinterpret_cast<NwWarp *>(nw_smem)[threadIdx.x >> 5];
+    NwWarp<NW_CAP> &S = reinterpret_cast<NwWarp<NW_CAP> *>(nw_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     // warp-uniform totals (every lane holds the same numbers)
-    unsigned long long t_nodes = 0, t_leaves = 0, t_splits = 0, t_small = 0, t_rootleaf = 0;
+    unsigned long long t_nodes = 0, t_leaves = 0, t_splits = 0, t_small = 0;
     bool overflow = false;
+    const int64_t n_walk = (int64_t)__reduce_add_sync(NW_FULL, a.bins[lane]);
 
     for (;;) {
         unsigned long long b = 0;
@@ -207,59 +350,19 @@ near_walk(const NearArgs a)
             b = atomicAdd(a.counters + 6, 1ull);
         b = __shfl_sync(NW_FULL, b, 0);
         const int64_t i0 = (int64_t)b * a.batch;
-        if (i0 >= a.n_pairs)
+        if (i0 >= n_walk)
             break;
-        const int nb = (int)((a.n_pairs - i0) < a.batch ? (a.n_pairs - i0) : a.batch);
-
-        // ---- roots of the batch, one per lane --------------------------------------------------
-        int root_code = 0, root_small = 0;
-        double dens0 = 0.0, dens1 = 0.0;
-        const bool have = lane < nb;
-        if (have) {
-            const unsigned long long key = a.keys[i0 + lane];
-            const int64_t pi = (int64_t)(key >> 32), q = (int64_t)(key & 0xffffffffull);
-            const int64_t t = a.table.parent[q];
-            const int kind = a.table.tess_kind[t];
-            if (kind != TVD_DENS_CONST) {
-                double p[TVD_NPAR];
-#pragma unroll
-                for (int k = 0; k < TVD_NPAR; k++)
-                    p[k] = a.table.tess_params[TVD_NPAR * t + k];
-                const double top = a.table.top[q], bottom = a.table.bottom[q];
-                const double mr = 0.5 * (top + bottom + 2. * TVD_R), hdr = 0.5 * (top - bottom);
-                dens0 = tvd_density(kind, p, (hdr * -TVD_NODE + mr) - TVD_R);    // :274
-                dens1 = tvd_density(kind, p, (hdr * TVD_NODE + mr) - TVD_R);
-            }
-            PairCtx c;
-            make_pair_ctx(a, pi, q, t, c, dens0, dens1);
-            const double w = a.table.tess_bounds[6 * t + 0], e = a.table.tess_bounds[6 * t + 1];
-            const double s = a.table.tess_bounds[6 * t + 2], n = a.table.tess_bounds[6 * t + 3];
-            root_code = node_test(c, w, e, s, n, root_small);
-            if (root_code == 0) {
-                // the conservative far test deferred a pair whose root is integrated after all
-                a.pair_result[i0 + lane] = leaf_glq<FIELD>(c, w, e, s, n);
-            } else if (-1 + (root_code == 3 ? 4 : 2) > c.stack_size) {
-                overflow = true;        // stktop + new_cells > STACK_SIZE at the root (:88)
-            }
-        }
-        {
-            const unsigned m_have = __ballot_sync(NW_FULL, have);
-            const unsigned m_leaf = __ballot_sync(NW_FULL, have && root_code == 0);
-            t_nodes += __popc(m_have);
-            t_leaves += __popc(m_leaf);
-            t_rootleaf += __popc(m_leaf);
-            t_small += __reduce_add_sync(NW_FULL, (unsigned)root_small);
-        }
+        const int nb = (int)((n_walk - i0) < a.batch ? (n_walk - i0) : a.batch);
 
         // ---- the trees of the batch, one pair at a time -----------------------------------------
         for (int jp = 0; jp < nb; jp++) {
-            const int rc0 = __shfl_sync(NW_FULL, root_code, jp);
-            const double d0 = __shfl_sync(NW_FULL, dens0, jp), d1 = __shfl_sync(NW_FULL, dens1, jp);
-            if (rc0 == 0)
-                continue;
-            const unsigned long long key = a.keys[i0 + jp];
+            const int64_t ip = a.order[i0 + jp];
+            const int rc0 = a.root_code[ip];
+            const unsigned long long key = a.keys[ip];
             const int64_t pi = (int64_t)(key >> 32), q = (int64_t)(key & 0xffffffffull);
             const int64_t t = a.table.parent[q];
+            double d0, d1;
+            pair_densities(a, q, t, d0, d1);
             PairCtx c;
             make_pair_ctx(a, pi, q, t, c, d0, d1);
             unsigned p_nodes = 0, p_leaves = 0, p_splits = 0, p_small = 0;
@@ -399,7 +502,7 @@ near_walk(const NearArgs a)
             for (int o = 16; o > 0; o >>= 1)
                 acc += __shfl_xor_sync(NW_FULL, acc, o);
             if (lane == 0) {
-                a.pair_result[i0 + jp] = acc;
+                a.pair_result[ip] = acc;
                 if (a.leaf_counts)
                     atomicAdd(&a.leaf_counts[t * a.n_points + pi], (int)p_leaves - 1);
             }
@@ -422,15 +525,14 @@ near_walk(const NearArgs a)
         atomicAdd(&a.counters[3], t_small);
         if (overflow)
             atomicExch(&a.counters[4], 1ull);
-        atomicAdd(&a.counters[5], t_rootleaf);
     }
 }
 
-template <int FIELD>
-static cudaError_t launch_near_field(NearArgs a, cudaStream_t stream)
+template <int FIELD, int NW_CAP>
+static cudaError_t launch_near_walk(NearArgs a, cudaStream_t stream)
 {
     static int blocks_per_sm[64] = {0};
-    const size_t smem = sizeof(NwWarp) * NW_WARPS;
+    const size_t smem = sizeof(NwWarp<NW_CAP>) * NW_WARPS;
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess)
@@ -438,12 +540,13 @@ static cudaError_t launch_near_field(NearArgs a, cudaStream_t stream)
     if (dev < 0 || dev >= 64)
         return cudaErrorInvalidDevice;
     if (blocks_per_sm[dev] == 0) {
-        e = cudaFuncSetAttribute(near_walk<FIELD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem);
+        e = cudaFuncSetAttribute(near_walk<FIELD, NW_CAP>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, near_walk<FIELD>, 32 * NW_WARPS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, near_walk<FIELD, NW_CAP>,
+                                                          32 * NW_WARPS, smem);
         if (e != cudaSuccess)
             return e;
         blocks_per_sm[dev] = nb > 0 ? nb : 1;
@@ -452,18 +555,46 @@ static cudaError_t launch_near_field(NearArgs a, cudaStream_t stream)
     if (e != cudaSuccess)
         return e;
     const int64_t warps = (int64_t)sms * blocks_per_sm[dev] * NW_WARPS;
-    // batches of consecutive pairs per grab: 32 when there is plenty of work, fewer when the pairs
-    // would not keep every warp busy (the results do not depend on it)
-    int64_t batch = a.n_pairs / (4 * warps);
+    // pairs per grab: the deepest trees come first and are taken one at a time (the number of
+    // pairs that split is only known on the device; all pairs bound it)
+    int64_t batch = a.n_pairs / (64 * warps);
     batch = batch < 1 ? 1 : (batch > 32 ? 32 : batch);
     a.batch = (int)batch;
     const int64_t n_batches = (a.n_pairs + batch - 1) / batch;
     int64_t blocks = (n_batches + NW_WARPS - 1) / NW_WARPS;
     if (blocks > (int64_t)sms * blocks_per_sm[dev])
         blocks = (int64_t)sms * blocks_per_sm[dev];
-    near_walk<FIELD><<<(unsigned)blocks, 32 * NW_WARPS, smem, stream>>>(a);
-    tvd_count_launch();
+    near_walk<FIELD, NW_CAP><<<(unsigned)blocks, 32 * NW_WARPS, smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+template <int FIELD>
+static cudaError_t launch_near_field(NearArgs a, cudaStream_t stream)
+{
+    // workspace: code[n] klass[n] (bytes), then order[n] (int32), then bins[64] (uint32)
+    unsigned char *ws = reinterpret_cast<unsigned char *>(a.workspace);
+    const size_t n = (size_t)a.n_pairs;
+    const size_t off_order = ((2 * n + 15) / 16) * 16;
+    a.root_code = ws;
+    a.root_class = ws + n;
+    a.order = reinterpret_cast<int32_t *>(ws + off_order);
+    a.bins = reinterpret_cast<unsigned *>(ws + off_order + 4 * n);
+    cudaError_t e = cudaMemsetAsync(a.bins, 0, 64 * sizeof(unsigned), stream);
+    if (e != cudaSuccess)
+        return e;
+    near_roots<FIELD><<<(unsigned)((a.n_pairs + 127) / 128), 128, 0, stream>>>(a);
+    near_order<<<(unsigned)((a.n_pairs + 255) / 256), 256, 0, stream>>>(a);
+    tvd_count_launch(3);
+    if (a.ratio <= NW_RATIO_SMALL)
+        return launch_near_walk<FIELD, NW_CAP_SMALL>(a, stream);
+    return launch_near_walk<FIELD, NW_CAP_LARGE>(a, stream);
+}
+
+// bytes of NearArgs::workspace for n pairs
+size_t tvd_near_workspace_bytes(int64_t n_pairs)
+{
+    const size_t n = (size_t)n_pairs;
+    return ((2 * n + 15) / 16) * 16 + 4 * n + 64 * sizeof(unsigned) + 16;
 }
 
 cudaError_t tvd_launch_near(const NearArgs &a, cudaStream_t stream)

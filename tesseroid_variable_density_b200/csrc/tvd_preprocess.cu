@@ -1,6 +1,6 @@
 // tvd_preprocess.cu -- point-independent preprocessing kernels (sm_100a).
 //
-// K1  density-based radial discretisation, one thread per tesseroid
+// K1  density-based radial discretisation, one warp per tesseroid
 //     (reference: _density_based_discretization / _divider_calculation,
 //      code/tesseroid_density/tesseroid.py:237-300; NumPy semantics restated literally)
 // --  sweep order: tesseroids stably sorted by longitude extent (tvd_build_sweep_order)
@@ -8,6 +8,7 @@
 //     halves of distance_n_size (_tesseroid.pyx:104-123) and scale_nodes (:152-176), the density
 //     at the radial GLQ nodes (:274), the node weights, the far-test records per ratio set, the
 //     bounding spheres of the tiles and the per-piece constants of the one-height specialisation.
+#include <cstdlib>
 #include "tvd_internal.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -33,156 +34,256 @@ __device__ __forceinline__ bool isclose_default(double a, double b)
     return a == b;
 }
 
-// tesseroid.py:286-300
-__device__ void divider_calculation(double top, double bottom, int kind, const double *p,
-                                    double rho_min, double rho_max, double &divider,
-                                    double &max_diff)
+// One WARP per tesseroid.  The 101 density samples of an interval are spread over the lanes
+// (sample i on lane i mod 32), minima / maxima / the first maximum of |rho_n - line| are warp
+// reductions with NumPy's tie and NaN rules, and the FIFO of pending intervals
+// (tesseroid.py:267-282) is a per-warp array in shared memory that is appended to and never
+// wraps (a tesseroid of k pieces creates 2k - 1 intervals).
+#define K1_WARPS 4
+#define K1_MAX_IV (2 * TVD_MAX_K1_PIECES)
+#define K1_KEEP TVD_K1_KEEP     // pieces per tesseroid the count pass keeps for the emit pass
+#define K1_FULL 0xffffffffu
+
+struct K1Best {                 // running first-maximum (numpy.argmax) with NaN propagation
+    double best;                // largest diff so far (-1 before the first sample)
+    int best_i;                 // its sample index (the smallest index among equals)
+    int nan_i;                  // index of the first NaN sample, 1000 if none
+};
+__device__ __forceinline__ void k1_best_merge(K1Best &a, double best, int best_i, int nan_i)
+{
+    if (best > a.best || (best == a.best && best_i < a.best_i)) {
+        a.best = best;
+        a.best_i = best_i;
+    }
+    if (nan_i < a.nan_i)
+        a.nan_i = nan_i;
+}
+
+// tesseroid.py:286-300, all lanes return the same divider and max_diff
+__device__ __forceinline__ void divider_calculation(int lane, double top, double bottom, int kind,
+                                                    const double *p, double rho_min,
+                                                    double rho_max, double &divider,
+                                                    double &max_diff)
 {
     const double delta = top - bottom;
     const double step = delta / 100.0;
     const double range = rho_max - rho_min;
-    const double nd0 = (tvd_density_cr(kind, p, bottom) - rho_min) / range;   // heights[0] == start
-    const double nd100 = (tvd_density_cr(kind, p, top) - rho_min) / range;
+    double nd[4], h[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = lane + 32 * j;
+        h[j] = linspace101(bottom, top, delta, step, i <= 100 ? i : 100);
+        nd[j] = (tvd_density_cr(kind, p, h[j]) - rho_min) / range;
+    }
+    const double nd0 = __shfl_sync(K1_FULL, nd[0], 0);       // heights[0] == bottom exactly
+    const double nd100 = __shfl_sync(K1_FULL, nd[3], 4);     // sample 100 = lane 4, slot 3
     const double slope = (nd100 - nd0) / (top - bottom);
-    double best = -1.0, best_h = bottom;
-    bool has_nan = false;
-    for (int i = 0; i < 101; i++) {
-        const double h = linspace101(bottom, top, delta, step, i);
-        const double nd = (tvd_density_cr(kind, p, h) - rho_min) / range;
-        const double line = slope * (h - bottom) + nd0;
-        const double diff = fabs(nd - line);
+    K1Best b = {-1.0, 1000, 1000};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = lane + 32 * j;
+        if (i > 100)
+            continue;
+        const double line = slope * (h[j] - bottom) + nd0;
+        const double diff = fabs(nd[j] - line);
         if (diff != diff) {                 // numpy max/argmax propagate the first NaN
-            if (!has_nan) {
-                has_nan = true;
-                best_h = h;
-            }
-        } else if (!has_nan && diff > best) {
-            best = diff;
-            best_h = h;
+            if (i < b.nan_i)
+                b.nan_i = i;
+        } else if (diff > b.best) {
+            b.best = diff;
+            b.best_i = i;
         }
     }
-    max_diff = has_nan ? nan("") : best;
-    divider = best_h;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(K1_FULL, b.best, o);
+        const int oi = __shfl_xor_sync(K1_FULL, b.best_i, o);
+        const int on = __shfl_xor_sync(K1_FULL, b.nan_i, o);
+        k1_best_merge(b, ob, oi, on);
+    }
+    if (b.nan_i <= 100) {
+        max_diff = nan("");
+        divider = linspace101(bottom, top, delta, step, b.nan_i);
+    } else {
+        max_diff = b.best;
+        divider = linspace101(bottom, top, delta, step, b.best_i);
+    }
 }
 
-// heights[0] of linspace is start only when the multiply-add leaves it untouched:
-// 0*step + start == start always (step finite), so nd0 above is exact.
-
+// EMIT = false: counts[t] = number of pieces, and the pieces themselves into `keep` when there
+// are at most K1_KEEP of them; EMIT = true: pieces written at offsets[t] (copied from `keep`
+// when the count pass stored them, recomputed otherwise).
 template <bool EMIT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * K1_WARPS)
 k1_discretize(int64_t n_tess, const double *__restrict__ bounds, const int32_t *__restrict__ kinds,
               const double *__restrict__ params, double delta, int has_delta,
               int32_t *__restrict__ counts, const int64_t *__restrict__ offsets,
               double *__restrict__ out_top, double *__restrict__ out_bottom,
-              int32_t *__restrict__ out_parent, int *__restrict__ status)
+              int32_t *__restrict__ out_parent, int *__restrict__ status,
+              double *__restrict__ keep)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_top[K1_WARPS][K1_MAX_IV], s_bot[K1_WARPS][K1_MAX_IV];
+    __shared__ unsigned char s_emit[K1_WARPS][K1_MAX_IV];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t t = (int64_t)blockIdx.x * K1_WARPS + wib;
     if (t >= n_tess)
         return;
     const double top = bounds[6 * t + 4], bottom = bounds[6 * t + 5];
+    int64_t base = 0;
+    if (EMIT) {
+        base = offsets[t];
+        const int cnt = counts[t];
+        if (cnt <= K1_KEEP) {               // the count pass kept them
+            if (lane < cnt) {
+                out_top[base + lane] = keep[(t * K1_KEEP + lane) * 2 + 0];
+                out_bottom[base + lane] = keep[(t * K1_KEEP + lane) * 2 + 1];
+                out_parent[base + lane] = (int32_t)t;
+            }
+            return;
+        }
+    }
     const int kind = kinds[t];
     double p[TVD_NPAR];
 #pragma unroll
     for (int i = 0; i < TVD_NPAR; i++)
         p[i] = params[TVD_NPAR * t + i];
-    int64_t base = 0;
-    if (EMIT)
-        base = offsets[t];
-    int nout = 0;
     bool single = (kind == TVD_DENS_CONST) || !has_delta;   // tesseroid.py:222
     double rho_min = 0, rho_max = 0;
     if (!single) {
         // tesseroid.py:258-264
         const double d = top - bottom, step = d / 100.0;
         bool has_nan = false;
-        rho_min = rho_max = tvd_density_cr(kind, p, bottom);
-        for (int i = 0; i < 101; i++) {
+        double lo = __longlong_as_double(0x7ff0000000000000ll), hi = -lo;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = lane + 32 * j;
+            if (i > 100)
+                continue;
             const double rho = tvd_density_cr(kind, p, linspace101(bottom, top, d, step, i));
             if (rho != rho)
                 has_nan = true;
-            if (rho < rho_min)
-                rho_min = rho;
-            if (rho > rho_max)
-                rho_max = rho;
+            if (rho < lo)
+                lo = rho;
+            if (rho > hi)
+                hi = rho;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double olo = __shfl_xor_sync(K1_FULL, lo, o), ohi = __shfl_xor_sync(K1_FULL, hi, o);
+            if (olo < lo)
+                lo = olo;
+            if (ohi > hi)
+                hi = ohi;
+        }
+        has_nan = __any_sync(K1_FULL, has_nan);
+        rho_min = lo;
+        rho_max = hi;
+        // every sample NaN leaves +-inf here; the reference then has min = max = NaN as well
         if (has_nan)
             rho_min = rho_max = nan("");
         single = isclose_default(rho_min, rho_max);
     }
     if (single) {
-        if (EMIT) {
-            out_top[base] = top;
-            out_bottom[base] = bottom;
-            out_parent[base] = (int32_t)t;
-        } else {
-            counts[t] = 1;
+        if (lane == 0) {
+            if (EMIT) {
+                out_top[base] = top;
+                out_bottom[base] = bottom;
+                out_parent[base] = (int32_t)t;
+            } else {
+                counts[t] = 1;
+                keep[(t * K1_KEEP) * 2 + 0] = top;
+                keep[(t * K1_KEEP) * 2 + 1] = bottom;
+            }
         }
         return;
     }
-    // FIFO of pending intervals (tesseroid.py:267-282), circular buffer in local memory
-    double qt[TVD_MAX_K1_PIECES], qb[TVD_MAX_K1_PIECES];
+    // FIFO of pending intervals (tesseroid.py:267-282)
+    double *iv_top = s_top[wib], *iv_bot = s_bot[wib];
+    unsigned char *iv_emit = s_emit[wib];
     const double tesseroid_size = top - bottom;
-    int head = 0, npending = 1;
-    qt[0] = top;
-    qb[0] = bottom;
-    while (npending > 0) {
-        const double it = qt[head], ib = qb[head];
-        head = (head + 1) % TVD_MAX_K1_PIECES;
-        npending--;
+    int n_iv = 1, nout = 0;
+    if (lane == 0) {
+        iv_top[0] = top;
+        iv_bot[0] = bottom;
+    }
+    __syncwarp();
+    for (int head = 0; head < n_iv; head++) {
+        const double it = iv_top[head], ib = iv_bot[head];
         double divider, max_diff;
-        divider_calculation(it, ib, kind, p, rho_min, rho_max, divider, max_diff);
+        divider_calculation(lane, it, ib, kind, p, rho_min, rho_max, divider, max_diff);
         const double size_ratio = (it - ib) / tesseroid_size;
         if (max_diff * size_ratio > delta) {
+            const int npending = n_iv - head - 1;
             if (npending + 2 + nout > TVD_MAX_K1_PIECES) {
-                atomicExch(status, TVD_ERR_TOO_MANY_PIECES);
-                if (!EMIT)
-                    counts[t] = 0;
+                if (lane == 0) {
+                    atomicExch(status, TVD_ERR_TOO_MANY_PIECES);
+                    if (!EMIT)
+                        counts[t] = 0;
+                }
                 return;
             }
-            int tail = (head + npending) % TVD_MAX_K1_PIECES;
-            qt[tail] = it;
-            qb[tail] = divider;
-            tail = (tail + 1) % TVD_MAX_K1_PIECES;
-            qt[tail] = divider;
-            qb[tail] = ib;
-            npending += 2;
-        } else {
-            if (EMIT) {
-                out_top[base + nout] = it;
-                out_bottom[base + nout] = ib;
-                out_parent[base + nout] = (int32_t)t;
+            if (lane == 0) {
+                iv_top[n_iv] = it;
+                iv_bot[n_iv] = divider;
+                iv_top[n_iv + 1] = divider;
+                iv_bot[n_iv + 1] = ib;
+                iv_emit[head] = 0;
             }
+            n_iv += 2;
+        } else {
+            if (lane == 0)
+                iv_emit[head] = 1;
             nout++;
         }
+        __syncwarp();
     }
-    if (!EMIT)
+    if (!EMIT && lane == 0)
         counts[t] = nout;
+    if (EMIT || nout <= K1_KEEP) {
+        // emitted intervals in processing order = the reference's emission order
+        int rank0 = 0;
+        for (int i0 = 0; i0 < n_iv; i0 += 32) {
+            const int i = i0 + lane;
+            const bool em = i < n_iv && iv_emit[i] != 0;
+            const unsigned m = __ballot_sync(K1_FULL, em);
+            if (em) {
+                const int r = rank0 + __popc(m & ((1u << lane) - 1u));
+                if (EMIT) {
+                    out_top[base + r] = iv_top[i];
+                    out_bottom[base + r] = iv_bot[i];
+                    out_parent[base + r] = (int32_t)t;
+                } else {
+                    keep[(t * K1_KEEP + r) * 2 + 0] = iv_top[i];
+                    keep[(t * K1_KEEP + r) * 2 + 1] = iv_bot[i];
+                }
+            }
+            rank0 += __popc(m);
+        }
+    }
 }
 
 cudaError_t tvd_launch_k1_count(const PieceTable &t, double delta, int has_delta, int *d_status,
-                                cudaStream_t stream)
+                                double *d_keep, cudaStream_t stream)
 {
     if (t.n_tess == 0)
         return cudaSuccess;
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((t.n_tess + threads - 1) / threads);
-    k1_discretize<false><<<blocks, threads, 0, stream>>>(
+    const unsigned blocks = (unsigned)((t.n_tess + K1_WARPS - 1) / K1_WARPS);
+    k1_discretize<false><<<blocks, 32 * K1_WARPS, 0, stream>>>(
         t.n_tess, t.tess_bounds, t.tess_kind, t.tess_params, delta, has_delta, t.tess_npieces,
-        nullptr, nullptr, nullptr, nullptr, d_status);
+        nullptr, nullptr, nullptr, nullptr, d_status, d_keep);
     tvd_count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t tvd_launch_k1_emit(const PieceTable &t, const int64_t *d_offsets, double delta,
-                               int has_delta, cudaStream_t stream)
+                               int has_delta, double *d_keep, cudaStream_t stream)
 {
     if (t.n_tess == 0)
         return cudaSuccess;
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((t.n_tess + threads - 1) / threads);
-    k1_discretize<true><<<blocks, threads, 0, stream>>>(
-        t.n_tess, t.tess_bounds, t.tess_kind, t.tess_params, delta, has_delta, nullptr, d_offsets,
-        t.top, t.bottom, t.parent, nullptr);
+    const unsigned blocks = (unsigned)((t.n_tess + K1_WARPS - 1) / K1_WARPS);
+    k1_discretize<true><<<blocks, 32 * K1_WARPS, 0, stream>>>(
+        t.n_tess, t.tess_bounds, t.tess_kind, t.tess_params, delta, has_delta, t.tess_npieces,
+        d_offsets, t.top, t.bottom, t.parent, nullptr, d_keep);
     tvd_count_launch();
     return cudaGetLastError();
 }
@@ -287,22 +388,23 @@ cudaError_t tvd_build_sweep_order(PieceTable &t, cudaStream_t stream)
     if (t.sweep_piece != nullptr || t.n_pieces == 0)
         return cudaSuccess;
     const int64_t n = t.n_tess;
+    // stream-ordered temporaries (cudaMallocAsync pool): no device-wide synchronisation
     unsigned long long *key_a = nullptr, *key_b = nullptr;
     int32_t *idx_a = nullptr, *idx_b = nullptr, *cnt = nullptr;
     int64_t *off = nullptr;
     void *temp = nullptr;
     size_t temp_bytes = 0;
-    cudaError_t e = cudaMalloc(&t.sweep_piece, (size_t)t.n_pieces * sizeof(int32_t));
+    cudaError_t e = cudaMallocAsync(&t.sweep_piece, (size_t)t.n_pieces * sizeof(int32_t), stream);
     auto done = [&](cudaError_t err) {
-        cudaFree(key_a);
-        cudaFree(key_b);
-        cudaFree(idx_a);
-        cudaFree(idx_b);
-        cudaFree(cnt);
-        cudaFree(off);
-        cudaFree(temp);
+        cudaFreeAsync(key_a, stream);
+        cudaFreeAsync(key_b, stream);
+        cudaFreeAsync(idx_a, stream);
+        cudaFreeAsync(idx_b, stream);
+        cudaFreeAsync(cnt, stream);
+        cudaFreeAsync(off, stream);
+        cudaFreeAsync(temp, stream);
         if (err != cudaSuccess) {
-            cudaFree(t.sweep_piece);
+            cudaFreeAsync(t.sweep_piece, stream);
             t.sweep_piece = nullptr;
         }
         return err;
@@ -315,14 +417,14 @@ cudaError_t tvd_build_sweep_order(PieceTable &t, cudaStream_t stream)
         if (e != cudaSuccess)  \
             return done(e);    \
     } while (0)
-    SW_TRY(cudaMalloc(&key_a, n * sizeof(unsigned long long)));
-    SW_TRY(cudaMalloc(&key_b, n * sizeof(unsigned long long)));
-    SW_TRY(cudaMalloc(&idx_a, n * sizeof(int32_t)));
-    SW_TRY(cudaMalloc(&idx_b, n * sizeof(int32_t)));
-    SW_TRY(cudaMalloc(&cnt, n * sizeof(int32_t)));
-    SW_TRY(cudaMalloc(&off, (n + 1) * sizeof(int64_t)));
+    SW_TRY(cudaMallocAsync(&key_a, n * sizeof(unsigned long long), stream));
+    SW_TRY(cudaMallocAsync(&key_b, n * sizeof(unsigned long long), stream));
+    SW_TRY(cudaMallocAsync(&idx_a, n * sizeof(int32_t), stream));
+    SW_TRY(cudaMallocAsync(&idx_b, n * sizeof(int32_t), stream));
+    SW_TRY(cudaMallocAsync(&cnt, n * sizeof(int32_t), stream));
+    SW_TRY(cudaMallocAsync(&off, (n + 1) * sizeof(int64_t), stream));
     SW_TRY(tvd_sort_pairs(nullptr, temp_bytes, key_a, key_b, idx_a, idx_b, n, stream));
-    SW_TRY(cudaMalloc(&temp, temp_bytes ? temp_bytes : 16));
+    SW_TRY(cudaMallocAsync(&temp, temp_bytes ? temp_bytes : 16, stream));
     const unsigned blocks = (unsigned)((n + 255) / 256);
     // LSD: first by e, then (stably) by w
     sweep_keys<<<blocks, 256, 0, stream>>>(n, t.tess_bounds, 1, nullptr, key_a, idx_a);
@@ -334,7 +436,6 @@ cudaError_t tvd_build_sweep_order(PieceTable &t, cudaStream_t stream)
     sweep_expand<<<blocks, 256, 0, stream>>>(n, idx_a, t.tess_offset, off, t.sweep_piece);
     tvd_count_launch(4);
     SW_TRY(cudaGetLastError());
-    SW_TRY(cudaStreamSynchronize(stream));
 #undef SW_TRY
     return done(cudaSuccess);
 }
@@ -356,7 +457,7 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
             const int32_t *__restrict__ tess_kind, const double *__restrict__ tess_params,
             const double *__restrict__ ptop, const double *__restrict__ pbottom,
             const int32_t *__restrict__ parent, const int32_t *__restrict__ sweep_piece,
-            double *__restrict__ glq_rec, double *__restrict__ geom)
+            int period, double *__restrict__ glq_rec, double *__restrict__ geom)
 {
     // one thread per sweep position qs; q = the piece (model order) visited there
     const int64_t qs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,19 +479,30 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
     const double lont = TVD_D2R * 0.5 * (w + e);
     const double latt = TVD_D2R * 0.5 * (s + n);
     double sinlatt, coslatt, sinlont, coslont, sin_n, cos_n, sin_s, cos_s;
-    dd_sincos(latt, sinlatt, coslatt);
-    dd_sincos(lont, sinlont, coslont);
-    dd_sincos(TVD_D2R * n, sin_n, cos_n);
-    dd_sincos(TVD_D2R * s, sin_s, cos_s);
+    cr_sincos(latt, sinlatt, coslatt);
+    cr_sincos(lont, sinlont, coslont);
+    cr_sincos(TVD_D2R * n, sin_n, cos_n);
+    cr_sincos(TVD_D2R * s, sin_s, cos_s);
     const double rtop = top + TVD_R;
-    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * dd_cos(TVD_D2R * (e - w)));
-    const double Llat = rtop * acos(sin_n * sin_s + cos_n * cos_s);
+    const double arg_lon = sinlatt * sinlatt + (coslatt * coslatt) * cr_cos(TVD_D2R * (e - w));
+    const double arg_lat = sin_n * sin_s + cos_n * cos_s;
+    const double Llon = rtop * acos(arg_lon);
+    const double Llat = rtop * acos(arg_lat);
+    // The far test must hold for the sizes the REFERENCE computes.  L = rtop*acos(arg) with
+    // L ~ sqrt(2 (1 - arg)): a difference of a few ulp in arg (libm vs libdevice sin/cos/acos)
+    // moves L by ~4e-16 / (2 (1 - arg)) relative, which for very small cells exceeds the fixed
+    // 2e-6 guard of the threshold (1 - arg = 1.5e-10 for a 0.001 degree cell).  The sizes that
+    // enter the conservative test are therefore inflated by that conditioning (the near-field
+    // walk, tvd_near.cu, repeats the literal test for everything this defers).
+    const double ulon = 1.0e-15 / fmax(1.0 - arg_lon, 1.0e-16);
+    const double ulat = 1.0e-15 / fmax(1.0 - arg_lat, 1.0e-16);
     double *gm = geom + TVD_GEOM_REC * qs;
     gm[0] = rt * (coslatt * coslont);          // centre of the piece, geocentric Cartesian
     gm[1] = rt * (coslatt * sinlont);
     gm[2] = rt * sinlatt;
     gm[3] = rt * rt;
-    gm[4] = fmax(Llon, Llat);                  // fmax ignores a single NaN (a NaN size never splits)
+    // fmax ignores a single NaN (a NaN size never splits)
+    gm[4] = fmax(Llon * (1.0 + ulon), Llat * (1.0 + ulat));
 
     // scale_nodes (_tesseroid.pyx:162-175)
     const double dlon = e - w, dlat = n - s, dr = top - bottom;
@@ -402,7 +514,7 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
         lonc[i] = TVD_D2R * (0.5 * dlon * node + mlon);
         const double latc = TVD_D2R * (0.5 * dlat * node + mlat);
-        dd_sincos(latc, sinlatc[i], coslatc[i]);
+        cr_sincos(latc, sinlatc[i], coslatc[i]);
         rc[i] = (0.5 * dr * node + mr);
         rcsq[i] = rc[i] * rc[i];
         dens[i] = tvd_density_cr(kind, p, rc[i] - TVD_R);   // :274 (or the constant, :250)
@@ -427,11 +539,12 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
             g[10 + 2 * j + k] = dens[k] * kappa * scale;
         }
     }
-    // flags relative to the previous record of the same tile, two 32-bit words: [0] = same
+    // flags relative to the previous record (reset at every multiple of `period`, where groups
+    // and tiles of the sweep may start), two 32-bit words: [0] = same
     // tesseroid (a further radial piece) -> the sweep keeps its whole angular half; [1] = same
     // extent in longitude (bitwise equal w and e) -> it keeps the longitude part
     int same_tess = 0, same_lon = 0;
-    if ((qs % TVD_TILE) != 0) {
+    if ((qs % period) != 0) {
         const int64_t tp = parent[sweep_piece[qs - 1]];
         if (tp == t) {
             same_tess = 1;
@@ -454,7 +567,7 @@ k4_pack_glq(int64_t n_pieces, const double *__restrict__ tess_bounds,
 // deferred to the literal walk.
 __global__ void __launch_bounds__(128)
 k4_pack_test(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios,
-             double *__restrict__ test_rec)
+             double *__restrict__ test_rec, bool no_far)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_pieces)
@@ -467,7 +580,9 @@ k4_pack_test(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios
     tr[2] = gm[2];
     for (int f = 0; f < ratios.nf; f++) {
         const double thr = ratios.ratio[f] * gm[4];             // = max(ratio*Llon, ratio*Llat)
-        const double thr2 = thr * thr * (1.0 + 2e-6) + 2.0;     // NaN if both sizes are NaN
+        double thr2 = thr * thr * (1.0 + 2e-6) + 2.0;           // NaN if both sizes are NaN
+        if (no_far)
+            thr2 = __longlong_as_double(0x7ff8000000000000ll);
         tr[3 + f] = gm[3] - thr2;       // a NaN threshold defers every pair of the piece
     }
     for (int f = 3 + ratios.nf; f < trec; f++)
@@ -481,13 +596,25 @@ k4_pack_test(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios
 // d_pq^2 > thr_q^2 (1 + 2e-6) + 2 + (rounding slack): every per-pair far test of the tile passes.
 __global__ void __launch_bounds__(128)
 k4_pack_tiles(int64_t n_pieces, const double *__restrict__ geom, RatioList ratios,
-              double *__restrict__ tile_rec)
+              int64_t ppg, int tiles_per_group, int64_t n_tiles, double *__restrict__ tile_rec,
+              bool no_far)
 {
     const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t q0 = tile * TVD_TILE;
-    if (q0 >= n_pieces)
+    if (tile >= n_tiles)
         return;
-    const int64_t q1 = q0 + TVD_TILE < n_pieces ? q0 + TVD_TILE : n_pieces;
+    const int64_t g = tile / tiles_per_group, k = tile - g * tiles_per_group;
+    const int64_t q0 = g * ppg + k * TVD_TILE;
+    int64_t q1 = q0 + TVD_TILE;
+    if (q1 > (g + 1) * ppg)
+        q1 = (g + 1) * ppg;
+    if (q1 > n_pieces)
+        q1 = n_pieces;
+    double *tr = tile_rec + TVD_TILE_REC * tile;
+    if (q0 >= q1) {                     // a tile slot beyond the end of its group: never read
+        for (int f = 0; f < TVD_TILE_REC; f++)
+            tr[f] = 0.0;
+        return;
+    }
     double cx = 0.0, cy = 0.0, cz = 0.0;
     for (int64_t q = q0; q < q1; q++) {
         cx += geom[TVD_GEOM_REC * q + 0];
@@ -499,7 +626,7 @@ k4_pack_tiles(int64_t n_pieces, const double *__restrict__ geom, RatioList ratio
     cy *= inv;
     cz *= inv;
     double r2max = 0.0, lmax = 0.0;
-    bool bad = false;
+    bool bad = no_far;
     for (int64_t q = q0; q < q1; q++) {
         const double dx = geom[TVD_GEOM_REC * q + 0] - cx, dy = geom[TVD_GEOM_REC * q + 1] - cy;
         const double dz = geom[TVD_GEOM_REC * q + 2] - cz;
@@ -510,7 +637,6 @@ k4_pack_tiles(int64_t n_pieces, const double *__restrict__ geom, RatioList ratio
         r2max = fmax(r2max, r2);
         lmax = fmax(lmax, L);
     }
-    double *tr = tile_rec + TVD_TILE_REC * tile;
     tr[0] = cx;
     tr[1] = cy;
     tr[2] = cz;
@@ -528,7 +654,7 @@ k4_pack_tiles(int64_t n_pieces, const double *__restrict__ geom, RatioList ratio
     }
 }
 
-cudaError_t tvd_launch_pack_glq(const PieceTable &t, double *d_glq, double *d_geom,
+cudaError_t tvd_launch_pack_glq(const PieceTable &t, int period, double *d_glq, double *d_geom,
                                 cudaStream_t stream)
 {
     if (t.n_pieces == 0)
@@ -537,23 +663,44 @@ cudaError_t tvd_launch_pack_glq(const PieceTable &t, double *d_glq, double *d_ge
     const unsigned blocks = (unsigned)((t.n_pieces + threads - 1) / threads);
     k4_pack_glq<<<blocks, threads, 0, stream>>>(t.n_pieces, t.tess_bounds, t.tess_kind,
                                                 t.tess_params, t.top, t.bottom, t.parent,
-                                                t.sweep_piece, d_glq, d_geom);
+                                                t.sweep_piece, period, d_glq, d_geom);
     tvd_count_launch();
     return cudaGetLastError();
 }
 
+static bool tvd_debug_no_far()
+{
+    // test knob: every pair goes through the literal near-field walk (no far-field shortcut)
+    const char *nf = getenv("TVD_DEBUG_NO_FAR");
+    return nf && nf[0] == '1';
+}
+
 cudaError_t tvd_launch_pack_test(const PieceTable &t, const double *d_geom, RatioList ratios,
-                                 double *d_test, double *d_tile, cudaStream_t stream)
+                                 double *d_test, cudaStream_t stream)
 {
     if (t.n_pieces == 0)
         return cudaSuccess;
     const int threads = 128;
     const unsigned blocks = (unsigned)((t.n_pieces + threads - 1) / threads);
-    k4_pack_test<<<blocks, threads, 0, stream>>>(t.n_pieces, d_geom, ratios, d_test);
-    const int64_t n_tiles = (t.n_pieces + TVD_TILE - 1) / TVD_TILE;
+    k4_pack_test<<<blocks, threads, 0, stream>>>(t.n_pieces, d_geom, ratios, d_test,
+                                                 tvd_debug_no_far());
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t tvd_launch_pack_tiles(const PieceTable &t, const double *d_geom, RatioList ratios,
+                                  int64_t pieces_per_group, int n_groups, double *d_tile,
+                                  cudaStream_t stream)
+{
+    if (t.n_pieces == 0)
+        return cudaSuccess;
+    const int threads = 128;
+    const int tiles_per_group = (int)((pieces_per_group + TVD_TILE - 1) / TVD_TILE);
+    const int64_t n_tiles = (int64_t)n_groups * tiles_per_group;
     k4_pack_tiles<<<(unsigned)((n_tiles + threads - 1) / threads), threads, 0, stream>>>(
-        t.n_pieces, d_geom, ratios, d_tile);
-    tvd_count_launch(2);
+        t.n_pieces, d_geom, ratios, pieces_per_group, tiles_per_group, n_tiles, d_tile,
+        tvd_debug_no_far());
+    tvd_count_launch();
     return cudaGetLastError();
 }
 

@@ -46,3 +46,39 @@ def test_rank_compute_callable_uses_the_global_plan():
         got[s:e] = compute("gz", *[c[s:e] for c in cc])
     pm.close()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("field", ["gy", "gyy", "gxy", "gz", "potential"])
+def test_chunking_is_bit_exact_when_warps_straddle_pi_over_4(field):
+    """A point's value must not depend on which points share its warp.  The far-field sweep
+    picks its sin/cos code path by warp vote (tvd_far.cu: trig2): on a grid wider than pi/4 in
+    longitude, chunk starts that are not multiples of 32 change the composition of every warp
+    (ADVICE round 1).  Fields that use sin(lon' - lon) (gy, gxy, gyy, gyz) are the sensitive ones;
+    the reference's njobs chunking is bit-exact (tesseroid.py:188-192)."""
+    from tesseroid_variable_density_b200 import density as D
+    from tesseroid_variable_density_b200 import gridder
+    from tesseroid_variable_density_b200.mesher import TesseroidMesh
+    from tesseroid_variable_density_b200.tesseroid import PreparedModel, _convert_coords, forward_raw
+    mesh = TesseroidMesh((-20, 20, -15, 15, 0, -30000.), (1, 12, 16))
+    mesh.addprop("density", [D.ExponentialDensity.between(2670, 3300, 0., -30000., 3)] * mesh.size)
+    lats, lons, heights = gridder.regular((-80, 80, -170, 175), (37, 73), z=50e3)    # 2701 points
+    cc = _convert_coords(lons, lats, heights)
+    pm = PreparedModel(mesh, delta=0.1)
+    ratio = cases.DEFAULT_RATIO[field]
+    try:
+        one = forward_raw(field, *cc, pm, ratio)
+        for k in (3, 5, 7, 11):
+            assert (lons.size // k) % 32 != 0 or k == 3
+            many = forward_raw(field, *cc, pm, ratio, devices=[0] * k)
+            assert np.array_equal(one, many), (field, k, int(np.sum(one != many)))
+        # one NaN (and one huge) coordinate must not change any other point's value
+        lon2 = cc[0].copy()
+        lon2[40] = np.nan
+        lon2[41] = 3.0e6
+        bad = forward_raw(field, lon2, cc[1], cc[2], cc[3], pm, ratio)
+        keep = np.ones(lons.size, dtype=bool)
+        keep[40:42] = False
+        assert np.isnan(bad[40])
+        assert np.array_equal(bad[keep], one[keep])
+    finally:
+        pm.close()

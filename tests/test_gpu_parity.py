@@ -225,3 +225,52 @@ def test_notebook_cases(oracle_lib):
     res = run_both(oracle_lib, mesh, grid, ["potential", "gx", "gy", "gz"], 1e-2, counts=True)
     for field, (g, o, _, ceq, seq) in res.items():
         assert ceq and seq and np.max(np.abs(g - o)) <= 1e-9 * np.max(np.abs(o)), field
+
+
+@pytest.mark.parametrize("size_deg,safe_eps", [(1e-3, 1e-4), (1e-4, 1e-2), (1e-5, 0.5)])
+def test_tiny_cells_at_the_ratio_boundary(oracle_lib, monkeypatch, size_deg, safe_eps):
+    """Cells of 0.001 ... 0.00001 degree at distances d = D*L*(1 +- eps) from the point.
+    L = rtop*acos(arg) with 1 - arg ~ 1e-10 ... 1e-14 for such cells: a 1-ulp difference in arg
+    moves L by 7e-7 ... 7e-3, more than a fixed relative guard on the far-field test covers
+    (divisions, _tesseroid.pyx:129-146 with the sizes of :104-123).
+      * at |eps| >= safe_eps (10x the conditioning of L) the subdivision counts must be the
+        oracle's;
+      * at every eps, including 1e-9, the far-field shortcut must agree with the literal walk of
+        the same pair (TVD_DEBUG_NO_FAR=1 sends every pair through the walk)."""
+    from tesseroid_variable_density_b200.mesher import Tesseroid
+    R, D_ratio, d2r = 6378137.0, 2.5, np.pi / 180.
+    w, s = 10.0, 20.0
+    e, n = w + size_deg, s + size_deg
+    top = 0.0
+    bottom = -max(1.0, 1.1e5 * size_deg)
+    model = [Tesseroid(w, e, s, n, top, bottom, props={"density": 1000.})]
+    rt, rtop = 0.5 * (top + bottom) + R, top + R
+    latt = d2r * 0.5 * (s + n)
+    Llon = rtop * np.arccos(np.sin(latt) ** 2 + np.cos(latt) ** 2 * np.cos(d2r * (e - w)))
+    Llat = rtop * np.arccos(np.sin(d2r * n) * np.sin(d2r * s) + np.cos(d2r * n) * np.cos(d2r * s))
+    eps = np.array([1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 0.1, 0.5])
+    eps = np.concatenate([-eps[::-1], eps])
+    dist = np.concatenate([D_ratio * Llon * (1 + eps), D_ratio * Llat * (1 + eps)])
+    all_eps = np.concatenate([eps, eps])
+    lons = np.full(dist.size, 0.5 * (w + e))
+    lats = np.full(dist.size, 0.5 * (s + n))
+    heights = (rt - R) + dist
+    flat = flatten_model(model)
+    cc = _convert_coords(lons, lats, heights)
+    o = oracle_lib.forward("gz", flat.bounds, flat.kind, flat.params, 0.1, D_ratio, *cc,
+                           leaf_counts=True, n_threads=1)
+    pm = PreparedModel(model, delta=0.1)
+    g = forward_raw("gz", *cc, pm, D_ratio, leaf_counts=True, return_stats=True)
+    pm.close()
+    monkeypatch.setenv("TVD_DEBUG_NO_FAR", "1")
+    pm = PreparedModel(model, delta=0.1)
+    lit = forward_raw("gz", *cc, pm, D_ratio, leaf_counts=True, return_stats=True)
+    pm.close()
+    monkeypatch.delenv("TVD_DEBUG_NO_FAR")
+    assert lit[1]["near_pairs"] == dist.size
+    assert np.array_equal(g[2], lit[2])                 # shortcut == literal walk, every eps
+    assert np.allclose(g[0], lit[0], rtol=1e-9, atol=0)      # sweep vs walk arithmetic, 1e-9 bar
+    safe = np.abs(all_eps) >= safe_eps
+    assert np.array_equal(g[2][0][safe], o[2][0][safe]), (g[2][0][safe], o[2][0][safe])
+    assert np.max(np.abs(g[0][safe] - o[0][safe])) <= 1e-9 * np.max(np.abs(o[0][safe]))
+    assert len(set(o[2][0])) >= 2                       # the boundary is actually crossed
