@@ -54,6 +54,11 @@ SEED = 20190277
 F_PAIR_EXECUTED = 136.7
 F_PAIR_CALIBRATED = 218
 F_PAIR_V1_ESTIMATE = 384
+# static facts of the committed far-field kernel from its ncu capture (profiles/far_sweep_r2.md)
+FAR_TRAFFIC_BYTES = 370.1e6
+FAR_NCU = {"fp64_pipe_pct_of_peak": 86.8, "issue_active_pct": 59.9,
+           "executed_fp64_instructions_per_piece_pair": 96.4,
+           "executed_flops_per_piece_pair": 136.7}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -263,10 +268,74 @@ def workload_config(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def c4_model_object():
+    """The C4 model as a Python model OBJECT (TesseroidModel with a per-cell density list), the
+    form a user of the reference's call surface holds; used for the cold end-to-end number."""
+    from tesseroid_variable_density_b200.mesher import TesseroidModel
+    rng = np.random.default_rng(SEED)
+    thickness = rng.uniform(200, 6000, NLAT * NLON)
+    top = np.full(NLAT * NLON, 845.0)
+    model = TesseroidModel((-44.99, -25.01, 280.01, 299.99), top, top - thickness, (NLAT, NLON))
+    model.addprop("density", [c4_density()] * model.size)
+    return model
+
+
+def irregular_bounds(bounds, seed=7):
+    """C4 bounds with every tesseroid's longitude extent made distinct (jitter of 1e-7 deg):
+    no two records share (w, e), so the sweep recomputes the longitude half of the quadrature
+    for every tesseroid -- what an irregular (non-mesh) model costs."""
+    rng = np.random.default_rng(seed)
+    b = bounds.copy()
+    b[:, 0] += rng.uniform(-1e-7, 1e-7, b.shape[0])
+    b[:, 1] += rng.uniform(-1e-7, 1e-7, b.shape[0])
+    return b
+
+
+class Timer(object):
+    """CUDA-event timing on torch's current stream, max over ranks."""
+
+    def __init__(self, torch, dist, world, dev):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, n):
+        """device ms of `for i in range(n): fn(i)`, max over ranks"""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = torch.cuda.current_stream()
+        e0.record(stream)
+        for i in range(n):
+            fn(i)
+        e1.record(stream)
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def wall_max(self, seconds):
+        t = self.torch.tensor([seconds], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def phase_ms(lib, reset):
+    out = (C.c_double * 4)()
+    lib.tvd_phase_ms(1 if reset else 0, out)
+    return [float(v) for v in out]
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from tesseroid_variable_density_b200 import _lib
+    from tesseroid_variable_density_b200 import _lib, tesseroid
+    from tesseroid_variable_density_b200.model import FlatModel
     from tesseroid_variable_density_b200.tesseroid import (PreparedModel, _convert_coords,
                                                            forward_raw, STACK_SIZE)
 
@@ -276,9 +345,16 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # host-side barrier for the cold leg: ranks waiting in an NCCL barrier would spin on
+        # the GPUs that rank 0 is about to use
+        cpu_group = dist.new_group(backend="gloo")
     lib = _lib.load()
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    timer = Timer(torch, dist, world, dev)
 
     flat = c4_flat_model()
     prepared = PreparedModel(flat, delta=0.1, device=local)
@@ -290,90 +366,162 @@ def run_gpu(args):
     shard = n_total // world
     base = rank * shard
 
-    def slab(step):
+    def slab(step, z=None, jitter=False):
         start = base + (step * P) % max(1, shard - P + 1) if shard > P else base
         idx = (start + np.arange(P)) % n_total
-        return lons[idx], lats[idx], heights[idx]
+        h = heights[idx] if z is None else np.full(P, z)
+        if jitter:      # topography-following points: no two at the same height
+            h = h + np.random.default_rng(step).uniform(0.0, 500.0, P)
+        return lons[idx], lats[idx], h
 
-    n_steps_total = args.warmup + args.steps
-    dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
     stats = np.zeros(_lib.NSTATS, dtype=np.int64)
-    n_groups = lib.tvd_plan_groups(prepared.handle, P)
 
-    def device_step(d_pts, d_res):
+    def device_call(model, d_pts, d_res, n, n_groups):
         rc = lib.tvd_forward_device(
-            _lib.FIELDS["gz"], prepared.handle, local, P,
+            _lib.FIELDS["gz"], model.handle, local, n,
             d_pts[0].data_ptr(), d_pts[1].data_ptr(), d_pts[2].data_ptr(), d_pts[3].data_ptr(),
             2.5, STACK_SIZE, n_groups, d_res.data_ptr(), _lib.ptr_i64(stats),
             C.c_void_p(stream.cuda_stream))
         _lib.check(rc, "tvd_forward_device")
 
-    # inputs resident in HBM before the timed region
-    resident = []
-    for s in range(n_steps_total):
-        cc = _convert_coords(*slab(s))
-        resident.append(torch.from_numpy(np.stack(cc)).to(dev))
+    def to_device(cc):
+        return torch.from_numpy(np.stack(cc)).to(dev)
+
+    # ---- headline: weak-scaled slabs at 10 km, inputs resident in HBM ---------------------------
+    n_groups = lib.tvd_plan_groups(prepared.handle, P)
+    n_steps_total = args.warmup + args.steps
+    resident = [to_device(_convert_coords(*slab(s))) for s in range(n_steps_total)]
     d_res = torch.empty(P, dtype=torch.float64, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for s in range(args.warmup):
-        device_step(resident[s], d_res)
-    barrier()
+        device_call(prepared, resident[s], d_res, P, n_groups)
+    timer.barrier()
     lib.tvd_launch_count(1)
-    lib.tvd_far_kernel_ms(1, None)
+    phase_ms(lib, True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     agg = np.zeros(_lib.NSTATS, dtype=np.int64)
-    e0.record(stream)
-    for s in range(args.steps):
-        device_step(resident[args.warmup + s], d_res)
-        agg += stats
-    e1.record(stream)
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+
+    def step(i):
+        device_call(prepared, resident[args.warmup + i], d_res, P, n_groups)
+        agg.__iadd__(stats)
+    ms = timer.run(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(lib.tvd_launch_count(0))
-    nfar = C.c_int64(0)
-    far_ms = float(lib.tvd_far_kernel_ms(0, C.byref(nfar)))
+    far_ms, _, _, nfar = phase_ms(lib, True)
     checksum = float(d_res.sum().item())
+    del resident
 
-    # end to end through the public call surface with HOST buffers: _convert_coords on the
-    # host, H2D of the step's points and D2H of its result inside the timed region
+    # ---- end to end through the call surface with HOST buffers: _convert_coords on the host,
+    # H2D of the step's points and D2H of its result inside the timed region ---------------------
     for s in range(min(2, args.warmup)):
-        lo, la, he = slab(s)
-        forward_raw("gz", *_convert_coords(lo, la, he), prepared, 2.5, devices=[local])
-    barrier()
+        forward_raw("gz", *_convert_coords(*slab(s)), prepared, 2.5, devices=[local])
+    timer.barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        lo, la, he = slab(args.warmup + s)
-        out = forward_raw("gz", *_convert_coords(lo, la, he), prepared, 2.5, devices=[local])
+        forward_raw("gz", *_convert_coords(*slab(args.warmup + s)), prepared, 2.5, devices=[local])
     torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    t_e2e = timer.wall_max(time.perf_counter() - t0)
+
+    # ---- near-field workload: the same slabs at 2 km (millions of near-field pairs) -------------
+    near_steps = max(1, min(3, args.steps))
+    res2 = [to_device(_convert_coords(*slab(s, z=2e3))) for s in range(near_steps + 1)]
+    device_call(prepared, res2[0], d_res, P, n_groups)
+    phase_ms(lib, True)
+    agg2 = np.zeros(_lib.NSTATS, dtype=np.int64)
+
+    def step2(i):
+        device_call(prepared, res2[1 + i], d_res, P, n_groups)
+        agg2.__iadd__(stats)
+    ms2 = timer.run(step2, near_steps)
+    far2, near2, post2, _ = phase_ms(lib, True)
+    del res2
+
+    # ---- bracket of the headline: what an irregular model / topography-following points cost ----
+    bracket = {}
+    br_steps = max(1, min(2, args.steps))
+    irr = PreparedModel(FlatModel(irregular_bounds(flat.bounds), flat.kind, flat.params),
+                        delta=0.1, device=local)
+    for name, model, jitter in (("irregular_model", irr, False),
+                                ("topography_points", prepared, True),
+                                ("irregular_model_and_topography_points", irr, True)):
+        pts = [to_device(_convert_coords(*slab(s, jitter=jitter))) for s in range(br_steps + 1)]
+        device_call(model, pts[0], d_res, P, n_groups)
+        phase_ms(lib, True)
+        t = timer.run(lambda i: device_call(model, pts[1 + i], d_res, P, n_groups), br_steps)
+        f_ms = phase_ms(lib, True)[0]
+        bracket[name] = {"value": float(n_tess) * P * br_steps * world / (t * 1e-3), "unit": UNIT,
+                         "sweep_ms_per_step": f_ms / br_steps}
+        del pts
+    irr.close()
+
+    # ---- fixed-size (strong) scaling: the WHOLE 1000 x 1000 grid split over the ranks -----------
+    # contiguous chunks as _split_arrays (tesseroid.py:318-323), global summation plan
+    from tesseroid_variable_density_b200.distributed import shard_bounds
+    g_full = lib.tvd_plan_groups(prepared.handle, n_total)
+    lo, hi = shard_bounds(n_total, world, rank)
+    full_pts = to_device(_convert_coords(lons[lo:hi], lats[lo:hi], heights[lo:hi]))
+    full_res = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    device_call(prepared, resident_small(full_pts, 4096), full_res[:4096], 4096, g_full)   # warm-up
+    ms_strong = timer.run(lambda i: device_call(prepared, full_pts, full_res, hi - lo, g_full), 1)
+    # sharding check: rank 0 recomputes the first 4096 points of every rank's chunk (and, with
+    # one rank, a chunk that starts off a multiple of 32) and compares the bits
+    probe = 4096
+    mine = full_res[:probe].clone()
     if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    t_e2e = float(t_e2e.item())
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+    identical = True
+    if rank == 0:
+        checks = [(r, shard_bounds(n_total, world, r)[0]) for r in range(world)]
+        if world == 1:
+            checks = [(0, 0), (0, 100003)]
+        for r, start in checks:
+            pts = to_device(_convert_coords(lons[start:start + probe], lats[start:start + probe],
+                                            heights[start:start + probe]))
+            out = torch.empty(probe, dtype=torch.float64, device=dev)
+            device_call(prepared, pts, out, probe, g_full)
+            want = gathered[r] if world > 1 else full_res[start:start + probe]
+            identical = identical and bool(torch.equal(out, want.to(dev)))
+    del full_pts
+
+    # ---- cold end to end: tesseroid.gz(lon, lat, height, model, njobs=N) from a Python model
+    # OBJECT to the host result, wall clock, on rank 0 driving all N GPUs of the box in-process
+    # (the reference's njobs surface, tesseroid.py:179-195); the other ranks wait ------------------
+    timer.barrier()
+    del full_res, d_res
+    torch.cuda.empty_cache()
+    e2e_cold = None
+    if rank == 0 and not args.no_cold:
+        t0 = time.perf_counter()
+        model_obj = c4_model_object()
+        t_obj = time.perf_counter() - t0
+        njobs = min(world, lib.tvd_device_count())
+        t0 = time.perf_counter()
+        out = tesseroid.gz(lons, lats, heights, model_obj, ratio=2.5, delta=0.1, njobs=njobs)
+        t_cold = time.perf_counter() - t0
+        e2e_cold = {"seconds": t_cold, "value": float(n_tess) * n_total / t_cold, "unit": UNIT,
+                    "call": "tesseroid.gz(lon, lat, height, TesseroidModel(1e6 cells), njobs=%d)"
+                            % njobs,
+                    "points": int(n_total), "model_object_build_s": t_obj,
+                    "checksum": float(np.sum(out))}
+    if cpu_group is not None:
+        dist.barrier(group=cpu_group)
+    timer.barrier()
 
     if rank == 0:
         evals = float(n_tess) * P * args.steps * world
         value = evals / (ms * 1e-3)
-        # roofline of the dominant kernel (far-field sweep): algorithmic FP64 flops by the
-        # canonical convention divided by its CUDA-event duration on its launch stream
-        far_pairs = float(agg[_lib.STAT_NAMES.index("nodes")] - agg[_lib.STAT_NAMES.index("nonroot_nodes")]
-                          - agg[_lib.STAT_NAMES.index("near_pairs")])
+        si = _lib.STAT_NAMES.index
+        far_pairs = float(agg[si("nodes")] - agg[si("nonroot_nodes")] - agg[si("near_pairs")])
         achieved = far_pairs * F_PAIR_EXECUTED / (far_ms * 1e-3) / 1e12 if far_ms > 0 else None
         achieved_cal = far_pairs * F_PAIR_CALIBRATED / (far_ms * 1e-3) / 1e12 if far_ms > 0 else None
         achieved_v1 = far_pairs * F_PAIR_V1_ESTIMATE / (far_ms * 1e-3) / 1e12 if far_ms > 0 else None
         peak = float(lib.tvd_measure_fp64_peak(local, 8192))
+        near_leaves = float(agg2[si("leaves")] - (agg2[si("nodes")] - agg2[si("nonroot_nodes")]
+                                                  - agg2[si("near_pairs")]))
+        near_nodes = float(agg2[si("nonroot_nodes")] + agg2[si("near_pairs")])
+        strong_value = float(n_tess) * n_total / (ms_strong * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -384,17 +532,18 @@ def run_gpu(args):
             "nodes_per_eval": float(agg[0]) / (float(n_tess) * P * args.steps),
             "near_pairs_per_step": float(agg[7]) / args.steps,
             "piece_pairs_per_s": float(n_pieces) * P * args.steps * world / (ms * 1e-3),
+            "sweep_groups": int(n_groups),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if (achieved and peak > 0) else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this
-                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r1g.md);
+                         # kernel at the default shape (ncu --set full, profiles/far_sweep_r2.md);
                          # the algorithmic minimum is the piece records read once, 337 MB
-                         "traffic": 370.1e6 if P == 75776 else None,
+                         "traffic": FAR_TRAFFIC_BYTES if P == 75776 else None,
                          "kernel": "far_sweep<gz>",
-                         "kernel_ms_per_launch": far_ms / max(1, nfar.value),
+                         "kernel_ms_per_launch": far_ms / max(1.0, nfar),
                          "kernel_share_of_step": far_ms / ms,
                          "flops_per_piece_pair": F_PAIR_EXECUTED,
-                         "piece_pairs_per_launch": far_pairs / max(1, nfar.value),
+                         "piece_pairs_per_launch": far_pairs / max(1.0, nfar),
                          # the instruction mix (DADD/DMUL count 1 flop, DFMA 2) caps the flop
                          # fraction of a saturated FP64 pipe at 136.7 / (2 x 96.4) = 0.71
                          "frac_ceiling_of_this_instruction_mix": 0.71,
@@ -402,13 +551,32 @@ def run_gpu(args):
                          "achieved_with_survey_estimate_384": achieved_v1,
                          "peak_source": "DFMA microbenchmark run by this process "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
-                         # static facts of this kernel build from its ncu capture
-                         # (profiles/far_sweep_r1g.md); not measured by this run
-                         "ncu": {"fp64_pipe_pct_of_peak": 86.8, "issue_active_pct": 59.9,
-                                 "executed_fp64_instructions_per_piece_pair": 96.4,
-                                 "executed_flops_per_piece_pair": 136.7}},
+                         # static facts of this kernel build from its ncu capture; not measured
+                         # by this run
+                         "ncu": FAR_NCU},
             "e2e": {"value": float(n_tess) * P * args.steps * world / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": 4 * 8 * P, "d2h_bytes_per_step": 8 * P},
+            # second timed workload: the same slabs 2 km above the model (near-field pairs)
+            "near": {"workload": "same slabs at z = 2 km", "steps": near_steps,
+                     "value": float(n_tess) * P * near_steps * world / (ms2 * 1e-3), "unit": UNIT,
+                     "ms_per_step": ms2 / near_steps,
+                     "near_pairs_per_step": float(agg2[si("near_pairs")]) / near_steps,
+                     "walk_ms_per_step": near2 / near_steps,
+                     "walk_share_of_step": near2 / ms2 if ms2 > 0 else None,
+                     "after_sweep_ms_per_step": post2 / near_steps,
+                     "sweep_ms_per_step": far2 / near_steps,
+                     "near_leaves_per_s": near_leaves / (near2 * 1e-3) if near2 > 0 else None,
+                     "near_nodes_per_s": near_nodes / (near2 * 1e-3) if near2 > 0 else None,
+                     "slowdown_vs_10km": (ms2 / near_steps) / (ms / args.steps)},
+            # the headline rate assumes a regular mesh and points at one height
+            "bracket": bracket,
+            # fixed-size scaling: the whole 1e6-point grid split over the ranks, one pass
+            "strong": {"value": strong_value, "unit": UNIT, "seconds": ms_strong * 1e-3,
+                       "points_per_gpu": int(hi - lo), "sweep_groups": int(g_full),
+                       "efficiency_vs_weak_rate": strong_value / value,
+                       "sharding_bit_identical": identical},
+            "sharding_bit_identical": identical,
+            "e2e_cold": e2e_cold,
             "gpu_launches": launches, "clocks": clocks, "checksum": checksum,
         }
         if world == 1 and not args.no_cpu:
@@ -426,6 +594,11 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def resident_small(pts, n):
+    """the first n points of a resident [4][P] tensor as a contiguous [4][n] tensor"""
+    return pts[:, :n].contiguous()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -435,6 +608,7 @@ def main():
                     help="points per GPU per step (default 148 SMs x 4 blocks x 128 threads)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-sample"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "cpu-sample":

@@ -274,3 +274,33 @@ def test_tiny_cells_at_the_ratio_boundary(oracle_lib, monkeypatch, size_deg, saf
     assert np.array_equal(g[2][0][safe], o[2][0][safe]), (g[2][0][safe], o[2][0][safe])
     assert np.max(np.abs(g[0][safe] - o[0][safe])) <= 1e-9 * np.max(np.abs(o[0][safe]))
     assert len(set(o[2][0])) >= 2                       # the boundary is actually crossed
+
+
+def test_c5_geometry_fused_fields(oracle_lib):
+    """BASELINE.json configs[4] (SURVEY.md 8d "C5") at a size the oracle finishes: a global
+    60 x 120 crust of per-cell sinusoidal densities (two periods over each cell's own
+    thickness, ~5 radial pieces per cell), potential + gz + gzz at 260 km in one fused sweep
+    (ratios 1 / 2.5 / 8), against the oracle field by field: counters identical, values
+    <= 1e-9 (potential, gz) and <= 1e-6 (gzz, l^-5-conditioned) relative."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "scripts"))
+    from c5_full import c5_model, c5_grid, NAMES, RATIOS
+    from tesseroid_variable_density_b200.tesseroid import forward_raw_fused
+    flat = c5_model(60, 120)
+    lon, lat, h = c5_grid(12, 24, 260e3)
+    cc = _convert_coords(lon, lat, h)
+    pm = PreparedModel(flat, delta=0.1)
+    try:
+        assert pm.n_pieces > 4 * flat.size
+        out, st = forward_raw_fused(NAMES, *cc, pm, RATIOS, return_stats=True)
+        for f, r, tol in zip(NAMES, RATIOS, (1e-9, 1e-9, 1e-6)):
+            o, so = oracle_lib.forward(f, flat.bounds, flat.kind, flat.params, 0.1, r, *cc,
+                                       n_threads=8)
+            assert all(st[f][k] == so[k] for k in COUNT_KEYS), f
+            rel = np.max(np.abs(out[f] - o)) / np.max(np.abs(o))
+            assert rel <= tol, "%s: rel %.3e" % (f, rel)
+            single, _ = forward_raw(f, *cc, pm, r, return_stats=True)
+            assert np.max(np.abs(single - out[f])) <= 1e-13 * np.max(np.abs(o))
+    finally:
+        pm.close()
