@@ -83,6 +83,12 @@ typedef struct tvd_model tvd_model;   /* opaque: flattened radial-piece table, p
 /* Number of visible CUDA devices (0 if none). */
 int tvd_device_count(void);
 
+/* Create the CUDA contexts of the given devices (NULL = 0..n_devices-1) concurrently.  Optional:
+ * contexts are otherwise created by the first call that uses a device; a caller that knows its
+ * devices can overlap this with its own preparation (the Python layer does so while it flattens
+ * the model, the counterpart of the reference forking its pool, tesseroid.py:180). */
+int tvd_warm_devices(int n_devices, const int *device_ids);
+
 /* Text of the last error raised on the calling thread ("" if none). */
 const char *tvd_last_error(void);
 

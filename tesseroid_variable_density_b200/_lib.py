@@ -32,6 +32,7 @@ _lp = C.POINTER(C.c_int64)
 SIGNATURES = {
     "tvd_device_count": (C.c_int, []),
     "tvd_last_error": (C.c_char_p, []),
+    "tvd_warm_devices": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "tvd_model_create": (C.c_int, [C.c_int64, _dp, _ip, _dp, C.c_double, C.c_int,
                                    C.POINTER(C.c_void_p)]),
     "tvd_model_free": (None, [C.c_void_p]),

@@ -413,6 +413,29 @@ extern "C" int tvd_device_count(void)
 
 extern "C" const char *tvd_last_error(void) { return g_last_error.c_str(); }
 
+extern "C" int tvd_warm_devices(int n_devices, const int *device_ids)
+{
+    // CUDA contexts are created lazily, ~0.3 s each; creating those of all devices at once (and
+    // while the caller is still flattening its model) takes them off the first call's critical path
+    const int avail = tvd_device_count();
+    if (n_devices < 1 || avail == 0)
+        return TVD_OK;
+    std::vector<std::thread> threads;
+    for (int d = 0; d < n_devices; d++) {
+        const int id = device_ids ? device_ids[d] : d;
+        if (id < 0 || id >= avail)
+            continue;
+        threads.emplace_back([id]() {
+            if (cudaSetDevice(id) == cudaSuccess)
+                cudaFree(nullptr);
+            cudaGetLastError();
+        });
+    }
+    for (auto &t : threads)
+        t.join();
+    return TVD_OK;
+}
+
 extern "C" int64_t tvd_launch_count(int reset)
 {
     if (reset)

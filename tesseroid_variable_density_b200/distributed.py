@@ -99,6 +99,10 @@ def make_gpu_compute(prepared, ratio, n_points_total, device=None):
                                     out.data_ptr(), _lib.ptr_i64(stats),
                                     C.c_void_p(stream.cuda_stream))
         _lib.check(rc, "tvd_forward_device")
+        if stats[3] != 0:       # same RuntimeWarning as the reference (tesseroid.py:227-228)
+            import warnings
+            from .tesseroid import _WARNING_MSG
+            warnings.warn(_WARNING_MSG, RuntimeWarning)
         return out.cpu().numpy()
 
     return compute

@@ -70,40 +70,61 @@ def _is_number(d):
 
 
 def _densities_to_arrays(dens_seq, n):
-    """kind/params arrays (and a keep mask) for a per-cell density sequence of length n."""
+    """kind/params arrays (and a keep mask) for a per-cell density sequence: cell ``i`` has
+    density ``dens_seq[i]`` (the reference indexes ``props['density'][index]``,
+    fatiando.mesher); ``None`` entries are skipped like cells without a density
+    (tesseroid.py:149-152)."""
     keep = np.ones(n, dtype=bool)
     if isinstance(dens_seq, DensityTable):
         assert len(dens_seq) == n
         return dens_seq.kind, dens_seq.params, keep
     if n == 0:
         return np.zeros(0, dtype=np.int32), np.zeros((0, _density.NPAR)), keep
-    # all numbers: constant densities, vectorised
+    assert len(dens_seq) >= n, "fewer densities ({}) than cells ({})".format(len(dens_seq), n)
+    # a numeric array: constant densities, vectorised
     if isinstance(dens_seq, np.ndarray) and dens_seq.dtype != object:
-        if dens_seq.shape == (n,) and np.issubdtype(dens_seq.dtype, np.number):
-            params = np.zeros((n, _density.NPAR))
-            params[:, 0] = dens_seq
-            return np.zeros(n, dtype=np.int32), params, keep
-    elif _is_number(dens_seq[0]):
+        if not np.issubdtype(dens_seq.dtype, np.number):
+            raise TypeError("unsupported density array of dtype {}".format(dens_seq.dtype))
+        params = np.zeros((n, _density.NPAR))
+        params[:, 0] = np.asarray(dens_seq, dtype=np.float64).reshape(len(dens_seq), -1)[:n, 0]
+        return np.zeros(n, dtype=np.int32), params, keep
+    # anything else is held as a list for the rest of this function: object identities are only
+    # meaningful while the objects are alive (iterating an array creates temporaries)
+    seq = dens_seq if isinstance(dens_seq, (list, tuple)) else list(dens_seq)
+    if len(seq) > n:
+        seq = seq[:n]
+    first = seq[0]
+    if first is not None and seq.count(first) == n:
+        # one density shared by every cell (the scripts' ``[density] * mesh.size``)
+        k, p = _density.as_kind_params(first)
+        return (np.full(n, k, dtype=np.int32), np.tile(np.asarray(p, dtype=np.float64), (n, 1)),
+                keep)
+    if _is_number(first):
         try:
-            arr = np.array(dens_seq, dtype=np.float64)
+            arr = np.array(seq, dtype=np.float64)
         except (TypeError, ValueError):
             arr = None
-        if arr is not None and arr.shape == (n,):
+        if arr is not None and arr.shape == (n,) and not any(d is None for d in seq):
             params = np.zeros((n, _density.NPAR))
             params[:, 0] = arr
             return np.zeros(n, dtype=np.int32), params, keep
     # objects: convert every DISTINCT object once (a mesh of a million cells usually shares a
     # handful of density objects) and scatter with NumPy
-    ids = np.fromiter((id(d) for d in dens_seq), dtype=np.int64, count=n)
-    uniq, first, inverse = np.unique(ids, return_index=True, return_inverse=True)
-    tab_kind = np.empty(uniq.size, dtype=np.int32)
+    ids = np.fromiter(map(id, seq), dtype=np.int64, count=n)
+    uniq, first_at, inverse = np.unique(ids, return_index=True, return_inverse=True)
+    tab_kind = np.zeros(uniq.size, dtype=np.int32)
     tab_params = np.zeros((uniq.size, _density.NPAR))
-    for u, i in enumerate(first):
-        k, p = _density.as_kind_params(dens_seq[int(i)])
+    tab_keep = np.ones(uniq.size, dtype=bool)
+    for u, i in enumerate(first_at):
+        d = seq[int(i)]
+        if d is None:
+            tab_keep[u] = False
+            continue
+        k, p = _density.as_kind_params(d)
         tab_kind[u] = k
         tab_params[u] = p
     inverse = inverse.reshape(-1)
-    return tab_kind[inverse], tab_params[inverse], keep
+    return tab_kind[inverse], tab_params[inverse], keep & tab_keep[inverse]
 
 
 def flatten_model(model, dens=None):
@@ -132,7 +153,8 @@ def flatten_model(model, dens=None):
             keep = np.zeros(n, dtype=bool)
             kind = np.zeros(n, dtype=np.int32)
             params = np.zeros((n, _density.NPAR))
-        bounds, kind, params = bounds[keep], kind[keep], params[keep]
+        if not keep.all():
+            bounds, kind, params = bounds[keep], kind[keep], params[keep]
         _check_bounds(bounds)
         return FlatModel(bounds, kind, params)
     # generic iterable: the reference's loop (tesseroid.py:217-221)

@@ -74,6 +74,34 @@ def _convert_coords(lon, lat, height):
     return lon, sinlat, coslat, radius
 
 
+def _warm_devices_async(njobs, devices):
+    """Start creating the CUDA contexts of the devices a multi-GPU call will use while the model
+    is still being flattened (ctypes releases the GIL); returns the thread to join, or None."""
+    ids = list(devices) if devices is not None else list(range(int(njobs)))
+    if len(ids) < 2:
+        return None
+    import threading
+    lib = _lib.load()
+    arr = (C.c_int * len(ids))(*[int(d) for d in ids])
+    t = threading.Thread(target=lib.tvd_warm_devices, args=(len(ids), arr))
+    t.start()
+    return t
+
+
+def _check_prepared_args(model, dens, delta):
+    """A PreparedModel has its densities and radial discretisation baked in: `dens` and a
+    different `delta` cannot be honoured, and silently ignoring them would give the result of
+    another model."""
+    if not isinstance(model, PreparedModel):
+        return
+    if dens is not None:
+        raise ValueError("dens= cannot override the densities of a PreparedModel; build it with "
+                         "PreparedModel(model, dens=...)")
+    if delta is not DELTA and delta != model.delta and not (delta is None and model.delta is None):
+        raise ValueError("delta={!r} differs from the PreparedModel's delta={!r}; build it with "
+                         "PreparedModel(model, delta=...)".format(delta, model.delta))
+
+
 class PreparedModel(object):
     """
     A model flattened and preprocessed on the GPU (density-based radial discretisation done,
@@ -246,8 +274,12 @@ def fields(names, lon, lat, height, model, dens=None, ratios=None, njobs=1, pool
                          np.asarray(lat, dtype=np.float64).ravel(),
                          np.asarray(height, dtype=np.float64).ravel())
     own = not isinstance(model, PreparedModel)
+    _check_prepared_args(model, dens, delta)
+    warm = _warm_devices_async(njobs, devices) if own else None
     prepared = PreparedModel(model, dens=dens, delta=delta,
                              device=(devices[0] if devices else 0)) if own else model
+    if warm is not None:
+        warm.join()
     try:
         if len(names) > 1 and fused_supported(names):
             raw = forward_raw_fused(names, *cc, prepared, ratios, njobs=njobs, devices=devices)
@@ -279,6 +311,7 @@ def sensitivity(field, lon, lat, height, model, dens=None, ratio=None, delta=DEL
         np.asarray(lon, dtype=np.float64).ravel(), np.asarray(lat, dtype=np.float64).ravel(),
         np.asarray(height, dtype=np.float64).ravel())]
     own = not isinstance(model, PreparedModel)
+    _check_prepared_args(model, dens, delta)
     prepared = PreparedModel(model, dens=dens, delta=delta, device=device) if own else model
     try:
         n, nt = cc[0].size, prepared.n_tesseroids
@@ -313,8 +346,12 @@ def _dispatcher(field, lon, lat, height, model, **kwargs):
         np.asarray(lon, dtype=np.float64).ravel(), np.asarray(lat, dtype=np.float64).ravel(),
         np.asarray(height, dtype=np.float64).ravel())
     own = not isinstance(model, PreparedModel)
+    _check_prepared_args(model, dens, delta)
+    warm = _warm_devices_async(njobs, devices) if own else None
     prepared = PreparedModel(model, dens=dens, delta=delta,
                              device=(devices[0] if devices else 0)) if own else model
+    if warm is not None:
+        warm.join()
     try:
         out = forward_raw(field, lon_r, sinlat, coslat, radius, prepared, ratio, njobs=njobs,
                           devices=devices)
