@@ -16,22 +16,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from tesseroid_variable_density_b200 import (ExponentialDensity, LinearDensity, TesseroidModel,  # noqa: E402
+from tesseroid_variable_density_b200 import (ExponentialDensity, LinearDensity, datasets,  # noqa: E402
                                              gridder, tesseroid)
 
-GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN = os.path.join(ROOT, "tests", "golden")      # only for the optional comparison below
 
-# sediment thickness grid (117 x 91 cells of 0.05 deg; NaN outside the basin)
-d = np.load(os.path.join(GOLDEN, "neuquen_thickness.npz"))
-lat, lon, thickness = d["lat"], d["lon"], d["thickness"]
-shape = (117, 91)
-area = (lat.min(), lat.max(), lon.min(), lon.max())
-nans = np.isnan(thickness)
-# constant top of the layer (median topography over the basin, 845 m in the paper)
-top = np.where(nans, 0.0, 845.0761706691)
-bottom = np.where(nans, 0.0, 845.0761706691 - np.nan_to_num(thickness))
-basin = TesseroidModel(area, top, bottom, shape)
-layer_top, layer_bottom = basin.top[~nans].max(), basin.bottom[~nans].min()
+# data/sediment_thickness.dat (117 x 91 nodes of 0.05 deg; NaN outside the basin) -> sediment
+# layer with a constant top (median topography over the basin, 845 m in the paper)
+sediments = datasets.load_sediment_thickness(os.path.join(ROOT, "data", "sediment_thickness.dat"))
+basin, layer_top, layer_bottom = datasets.neuquen_basin_model(sediments)
 print("model: %d tesseroids, sediments between %.1f and %.1f m" % (basin.size, layer_top, layer_bottom))
 
 # computation grid at 10 km

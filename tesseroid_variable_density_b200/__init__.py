@@ -7,11 +7,11 @@ scratch for NVIDIA B200 (sm_100a): hand-written FP64 CUDA kernels behind a C ABI
     from tesseroid_variable_density_b200 import tesseroid
     gz = tesseroid.gz(lon, lat, height, model, ratio=2.5, delta=0.1)
 """
-from . import constants, density, gridder, mesher, model          # noqa: F401
+from . import constants, datasets, density, gridder, mesher, model  # noqa: F401
 from .density import LinearDensity, ExponentialDensity, SineDensity  # noqa: F401
 from .mesher import Tesseroid, TesseroidMesh, TesseroidModel        # noqa: F401
 from . import tesseroid                                            # noqa: F401
 
-__all__ = ["tesseroid", "density", "mesher", "gridder", "constants", "model",
+__all__ = ["tesseroid", "density", "mesher", "gridder", "constants", "model", "datasets",
            "LinearDensity", "ExponentialDensity", "SineDensity",
            "Tesseroid", "TesseroidMesh", "TesseroidModel"]

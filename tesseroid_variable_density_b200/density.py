@@ -142,3 +142,83 @@ def as_kind_params(density):
             "(LinearDensity, ExponentialDensity, SineDensity) or a number. There is no CPU "
             "fallback.")
     raise TypeError("unsupported density {!r}".format(density))
+
+
+def fit_density(func, top, bottom, rtol=1e-9):
+    """
+    Recognise a Python callable ``func(height)`` as one of the parametric density models on
+    ``[bottom, top]`` and return the corresponding number or :class:`Density` object.
+
+    The reference takes arbitrary callables (code/tesseroid_density/_tesseroid.pyx:274); the
+    GPU kernels need parameters.  This helper samples the callable, fits a constant, a linear,
+    an exponential (``A*exp(k*h) + C``) or a sinusoidal (``A*sin(k*h) + C``) model -- the four
+    families of the reference's scripts -- and accepts the first one that reproduces the
+    callable to `rtol` (relative to its largest magnitude) on 201 heights.  Raises ``TypeError``
+    otherwise.  The fitted parameters agree with the callable's own to ~1e-12, so results differ
+    from a run with the exact density object at that level; where bit-level agreement with the
+    reference matters, pass the density object itself.
+    """
+    top, bottom = float(top), float(bottom)
+    if not top > bottom:
+        raise ValueError("fit_density needs top > bottom")
+    h = np.linspace(bottom, top, 201)
+    try:
+        f = np.asarray(func(h), dtype=np.float64)
+        if f.shape != h.shape:
+            raise ValueError
+    except Exception:
+        f = np.array([float(func(float(v))) for v in h])
+    scale = float(np.max(np.abs(f)))
+    if not np.all(np.isfinite(f)):
+        raise TypeError("density callable returns non-finite values on [bottom, top]")
+
+    def ok(model):
+        return float(np.max(np.abs(model(h) - f))) <= rtol * max(scale, 1e-300)
+
+    if np.all(f == f[0]):
+        return float(f[0])
+    lin = LinearDensity((f[-1] - f[0]) / (top - bottom), -bottom, f[0])
+    if ok(lin):
+        return lin
+    # A*exp(k*h) + C from three equally spaced samples: (f2 - f1)/(f1 - f0) = exp(k*dh)
+    i0, i1, i2 = 0, 100, 200
+    d1, d2 = f[i1] - f[i0], f[i2] - f[i1]
+    if d1 != 0 and d2 / d1 > 0 and d2 != d1:
+        k = np.log(d2 / d1) / (h[i1] - h[i0])
+        amp = d1 / np.expm1(k * (h[i1] - h[i0]))         # A*exp(k*bottom)
+        cand = ExponentialDensity(amp, k * (top - bottom), bottom, top - bottom, f[i0] - amp)
+        if ok(cand):
+            return cand
+        try:
+            from scipy.optimize import least_squares
+            sol = least_squares(lambda p: p[0] * np.exp(p[1] * (h - bottom) / (top - bottom)) + p[2] - f,
+                                [amp, k * (top - bottom), f[i0] - amp], xtol=1e-15, ftol=1e-15,
+                                gtol=1e-15)
+            cand = ExponentialDensity(sol.x[0], sol.x[1], bottom, top - bottom, sol.x[2])
+            if ok(cand):
+                return cand
+        except Exception:
+            pass
+    # A*sin(k*h) + C: dominant frequency from the spectrum, then least squares
+    try:
+        from scipy.optimize import least_squares
+        g = f - f.mean()
+        spec = np.abs(np.fft.rfft(g * np.hanning(g.size), 8 * g.size))
+        freq = np.fft.rfftfreq(8 * g.size, d=h[1] - h[0])
+        k0 = 2 * np.pi * freq[int(np.argmax(spec[1:])) + 1]
+        best = None
+        for sign in (1.0, -1.0):
+            sol = least_squares(lambda p: p[0] * np.sin(p[1] * h) + p[2] - f,
+                                [sign * 0.5 * (f.max() - f.min()), k0, f.mean()], xtol=1e-15,
+                                ftol=1e-15, gtol=1e-15, x_scale=[scale, k0, scale])
+            cand = SineDensity(sol.x[0], sol.x[1], sol.x[2])
+            if ok(cand) and (best is None):
+                best = cand
+        if best is not None:
+            return best
+    except Exception:
+        pass
+    raise TypeError(
+        "the density callable is not a constant, linear, exponential (A*exp(k*h) + C) or "
+        "sinusoidal (A*sin(k*h) + C) function of height on [{}, {}]; arbitrary callables "
+        "cannot be evaluated on the GPU and there is no CPU fallback".format(bottom, top))
