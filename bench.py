@@ -423,28 +423,34 @@ def run_gpu(args):
     torch.cuda.synchronize()
     t_e2e = timer.wall_max(time.perf_counter() - t0)
 
+    legs = set(x for x in args.legs.split(",") if x)
+    if args.no_cold:
+        legs.discard("cold")
     # ---- near-field workload: the same slabs at 2 km (millions of near-field pairs) -------------
-    near_steps = max(1, min(3, args.steps))
-    res2 = [to_device(_convert_coords(*slab(s, z=2e3))) for s in range(near_steps + 1)]
-    device_call(prepared, res2[0], d_res, P, n_groups)
-    phase_ms(lib, True)
+    near_steps = max(1, min(3, args.steps)) if "near" in legs else 0
     agg2 = np.zeros(_lib.NSTATS, dtype=np.int64)
+    ms2, far2, near2, post2 = 0.0, 0.0, 0.0, 0.0
+    if near_steps:
+        res2 = [to_device(_convert_coords(*slab(s, z=2e3))) for s in range(near_steps + 1)]
+        device_call(prepared, res2[0], d_res, P, n_groups)
+        phase_ms(lib, True)
 
-    def step2(i):
-        device_call(prepared, res2[1 + i], d_res, P, n_groups)
-        agg2.__iadd__(stats)
-    ms2 = timer.run(step2, near_steps)
-    far2, near2, post2, _ = phase_ms(lib, True)
-    del res2
+        def step2(i):
+            device_call(prepared, res2[1 + i], d_res, P, n_groups)
+            agg2.__iadd__(stats)
+        ms2 = timer.run(step2, near_steps)
+        far2, near2, post2, _ = phase_ms(lib, True)
+        del res2
 
     # ---- bracket of the headline: what an irregular model / topography-following points cost ----
     bracket = {}
     br_steps = max(1, min(2, args.steps))
     irr = PreparedModel(FlatModel(irregular_bounds(flat.bounds), flat.kind, flat.params),
-                        delta=0.1, device=local)
-    for name, model, jitter in (("irregular_model", irr, False),
-                                ("topography_points", prepared, True),
-                                ("irregular_model_and_topography_points", irr, True)):
+                        delta=0.1, device=local) if "bracket" in legs else None
+    for name, model, jitter in ((("irregular_model", irr, False),
+                                 ("topography_points", prepared, True),
+                                 ("irregular_model_and_topography_points", irr, True))
+                                if "bracket" in legs else ()):
         pts = [to_device(_convert_coords(*slab(s, jitter=jitter))) for s in range(br_steps + 1)]
         device_call(model, pts[0], d_res, P, n_groups)
         phase_ms(lib, True)
@@ -453,46 +459,22 @@ def run_gpu(args):
         bracket[name] = {"value": float(n_tess) * P * br_steps * world / (t * 1e-3), "unit": UNIT,
                          "sweep_ms_per_step": f_ms / br_steps}
         del pts
-    irr.close()
+    if irr is not None:
+        irr.close()
 
-    # ---- fixed-size (strong) scaling: the WHOLE 1000 x 1000 grid split over the ranks -----------
-    # contiguous chunks as _split_arrays (tesseroid.py:318-323), global summation plan
-    from tesseroid_variable_density_b200.distributed import shard_bounds
-    g_full = lib.tvd_plan_groups(prepared.handle, n_total)
-    lo, hi = shard_bounds(n_total, world, rank)
-    full_pts = to_device(_convert_coords(lons[lo:hi], lats[lo:hi], heights[lo:hi]))
-    full_res = torch.empty(hi - lo, dtype=torch.float64, device=dev)
-    device_call(prepared, resident_small(full_pts, 4096), full_res[:4096], 4096, g_full)   # warm-up
-    ms_strong = timer.run(lambda i: device_call(prepared, full_pts, full_res, hi - lo, g_full), 1)
-    # sharding check: rank 0 recomputes the first 4096 points of every rank's chunk (and, with
-    # one rank, a chunk that starts off a multiple of 32) and compares the bits
-    probe = 4096
-    mine = full_res[:probe].clone()
-    if world > 1:
-        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, gathered, dst=0)
-    identical = True
-    if rank == 0:
-        checks = [(r, shard_bounds(n_total, world, r)[0]) for r in range(world)]
-        if world == 1:
-            checks = [(0, 0), (0, 100003)]
-        for r, start in checks:
-            pts = to_device(_convert_coords(lons[start:start + probe], lats[start:start + probe],
-                                            heights[start:start + probe]))
-            out = torch.empty(probe, dtype=torch.float64, device=dev)
-            device_call(prepared, pts, out, probe, g_full)
-            want = gathered[r] if world > 1 else full_res[start:start + probe]
-            identical = identical and bool(torch.equal(out, want.to(dev)))
-    del full_pts
-
+    ms_strong, identical, g_full, lo, hi = None, None, None, 0, 0
+    if "strong" in legs:
+        ms_strong, identical, g_full, lo, hi = strong_leg(
+            torch, dist, lib, timer, prepared, device_call, to_device, _convert_coords, lons, lats,
+            heights, world, rank, dev)
     # ---- cold end to end: tesseroid.gz(lon, lat, height, model, njobs=N) from a Python model
     # OBJECT to the host result, wall clock, on rank 0 driving all N GPUs of the box in-process
     # (the reference's njobs surface, tesseroid.py:179-195); the other ranks wait ------------------
     timer.barrier()
-    del full_res, d_res
+    del d_res
     torch.cuda.empty_cache()
     e2e_cold = None
-    if rank == 0 and not args.no_cold:
+    if rank == 0 and "cold" in legs:
         t0 = time.perf_counter()
         model_obj = c4_model_object()
         t_obj = time.perf_counter() - t0
@@ -521,7 +503,7 @@ def run_gpu(args):
         near_leaves = float(agg2[si("leaves")] - (agg2[si("nodes")] - agg2[si("nonroot_nodes")]
                                                   - agg2[si("near_pairs")]))
         near_nodes = float(agg2[si("nonroot_nodes")] + agg2[si("near_pairs")])
-        strong_value = float(n_tess) * n_total / (ms_strong * 1e-3)
+        strong_value = float(n_tess) * n_total / (ms_strong * 1e-3) if ms_strong else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -557,7 +539,8 @@ def run_gpu(args):
             "e2e": {"value": float(n_tess) * P * args.steps * world / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": 4 * 8 * P, "d2h_bytes_per_step": 8 * P},
             # second timed workload: the same slabs 2 km above the model (near-field pairs)
-            "near": {"workload": "same slabs at z = 2 km", "steps": near_steps,
+            "near": None if not near_steps else {
+                     "workload": "same slabs at z = 2 km", "steps": near_steps,
                      "value": float(n_tess) * P * near_steps * world / (ms2 * 1e-3), "unit": UNIT,
                      "ms_per_step": ms2 / near_steps,
                      "near_pairs_per_step": float(agg2[si("near_pairs")]) / near_steps,
@@ -571,7 +554,8 @@ def run_gpu(args):
             # the headline rate assumes a regular mesh and points at one height
             "bracket": bracket,
             # fixed-size scaling: the whole 1e6-point grid split over the ranks, one pass
-            "strong": {"value": strong_value, "unit": UNIT, "seconds": ms_strong * 1e-3,
+            "strong": None if not ms_strong else {
+                       "value": strong_value, "unit": UNIT, "seconds": ms_strong * 1e-3,
                        "points_per_gpu": int(hi - lo), "sweep_groups": int(g_full),
                        "efficiency_vs_weak_rate": strong_value / value,
                        "sharding_bit_identical": identical},
@@ -594,6 +578,44 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def strong_leg(torch, dist, lib, timer, prepared, device_call, to_device, _convert_coords, lons,
+               lats, heights, world, rank, dev):
+    """Fixed-size (strong) scaling: the WHOLE 1000 x 1000 grid split over the ranks, one pass;
+    then the sharding check.  Returns (ms, bit_identical, n_groups, lo, hi)."""
+    n_total = lons.size
+    # contiguous chunks as _split_arrays (tesseroid.py:318-323), global summation plan
+    from tesseroid_variable_density_b200.distributed import shard_bounds
+    g_full = lib.tvd_plan_groups(prepared.handle, n_total)
+    lo, hi = shard_bounds(n_total, world, rank)
+    full_pts = to_device(_convert_coords(lons[lo:hi], lats[lo:hi], heights[lo:hi]))
+    full_res = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+    device_call(prepared, resident_small(full_pts, 4096), full_res[:4096], 4096, g_full)   # warm-up
+    ms_strong = timer.run(lambda i: device_call(prepared, full_pts, full_res, hi - lo, g_full), 1)
+    # sharding check: rank 0 recomputes the first 4096 points of every rank's chunk (and, with
+    # one rank, a chunk that starts off a multiple of 32) and compares the bits
+    probe = 4096
+    mine = full_res[:probe].clone()
+    if world > 1:
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+    identical = True
+    if rank == 0:
+        checks = [(r, shard_bounds(n_total, world, r)[0]) for r in range(world)]
+        if world == 1:
+            checks = [(0, 0), (0, 100003)]
+        for r, start in checks:
+            pts = to_device(_convert_coords(lons[start:start + probe], lats[start:start + probe],
+                                            heights[start:start + probe]))
+            out = torch.empty(probe, dtype=torch.float64, device=dev)
+            device_call(prepared, pts, out, probe, g_full)
+            want = gathered[r] if world > 1 else full_res[start:start + probe]
+            identical = identical and bool(torch.equal(out, want.to(dev)))
+    del full_pts
+
+    del full_res
+    return ms_strong, identical, g_full, lo, hi
+
+
 def resident_small(pts, n):
     """the first n points of a resident [4][P] tensor as a contiguous [4][n] tensor"""
     return pts[:, :n].contiguous()
@@ -609,6 +631,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-sample"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold end-to-end leg")
+    ap.add_argument("--legs", default="near,bracket,strong,cold",
+                    help="comma-separated extra legs after the headline and e2e measurements "
+                         "(profiling runs use fewer)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "cpu-sample":

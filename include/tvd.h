@@ -175,7 +175,8 @@ int tvd_forward_fused(int n_fields, const int *fields, const double *ratios, tvd
  * column at a time with `field(lon, lat, height, [tesseroid_t], dens=1)`
  * ("Use this, e.g., for sensitivity matrix building", tesseroid.py:347-349); row t here is
  * bit-identical to that call.  Single device; jac is a HOST buffer [n_tess][n_points], kernel
- * units.  Device memory needed: (n_pieces + n_tess) * n_points * 8 bytes.
+ * units.  The points are processed in slabs so that the device holds at most ~2 GiB of rows
+ * ((n_pieces + n_tess) * slab * 8 bytes).
  */
 int tvd_sensitivity(int field, tvd_model *model, int64_t n_points, const double *lon_rad,
                     const double *sinlat, const double *coslat, const double *radius,

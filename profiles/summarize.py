@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """
-Summarise an Nsight Compute report (.ncu-rep) of the far-field sweep into a small text file
-that can be committed (the .ncu-rep itself stays in gpurun_out/, which is scratch).
+Summarise an Nsight Compute report (.ncu-rep) into a small text file that can be committed (the
+.ncu-rep itself stays in gpurun_out/, which is scratch).
 
-    python profiles/summarize.py gpurun_out/prof_far_r1c.ncu-rep "<bench command>" > profiles/far_sweep_r1c.md
+    python profiles/summarize.py gpurun_out/prof_far_r2.ncu-rep "<ncu command line>" [units] [unit name] > profiles/far_sweep_r2.md
+
+`units` = number of work units of the launch ((piece, point) pairs for the sweep, nodes + leaves
+for the walk) for the per-unit instruction counts.
 """
 import csv
 import subprocess
@@ -12,7 +15,9 @@ import sys
 KEYS = [
     "gpu__time_duration.sum",
     "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-    "launch__shared_mem_per_block_static",
+    "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__cycles_active.avg",
     "sm__cycles_elapsed.avg", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
@@ -27,6 +32,7 @@ KEYS = [
     "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
     "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+    "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -43,8 +49,7 @@ def main():
     hdr, units = rows[0], rows[1]
     print("# ncu summary of `%s`" % rep.split("/")[-1])
     print()
-    print("command: `ncu --set full --clock-control none --import-source on -k regex:far_sweep "
-          "-s 3 -c 1 %s`" % cmd)
+    print("command: `%s`" % cmd)
     print()
     for r in rows[2:]:
         d = dict(zip(hdr, r))
@@ -56,6 +61,7 @@ def main():
             if k in d:
                 print("| %s | %s | %s |" % (k, d[k], units[hdr.index(k)]))
         pairs = float(sys.argv[3]) if len(sys.argv) > 3 else None
+        unit = sys.argv[4] if len(sys.argv) > 4 else "(piece, point) pair"
         try:
             cyc = float(d["smsp__cycles_elapsed.avg"]) if "smsp__cycles_elapsed.avg" in d \
                 else float(d["sm__cycles_elapsed.avg"])
@@ -68,10 +74,10 @@ def main():
                    ops["dadd"] + ops["dmul"] + 2 * ops["dfma"]))
             if pairs:
                 print()
-                print("per (piece, point) pair (%.4g pairs in this launch): DADD %.1f, DMUL %.1f, "
+                print("per %s (%.4g in this launch): DADD %.1f, DMUL %.1f, "
                       "DFMA %.1f = %.1f FP64 arithmetic instructions, %.1f hardware flops; "
-                      "all warp-instructions x32 / pair = %.1f" %
-                      (pairs, ops["dadd"] / pairs, ops["dmul"] / pairs, ops["dfma"] / pairs,
+                      "all warp-instructions x32 / unit = %.1f" %
+                      (unit, pairs, ops["dadd"] / pairs, ops["dmul"] / pairs, ops["dfma"] / pairs,
                        sum(ops.values()) / pairs,
                        (ops["dadd"] + ops["dmul"] + 2 * ops["dfma"]) / pairs,
                        float(d["smsp__inst_executed.sum"]) * 32 / pairs))

@@ -1359,20 +1359,44 @@ extern "C" int tvd_sensitivity(int field, tvd_model *m, int64_t n_points, const 
         return rc;
     std::lock_guard<std::mutex> lock(c->mu);
     CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(c->pts.reserve((size_t)P * 4 * sizeof(double), c->stream));
-    CUDA_TRY(c->jac_out.reserve((size_t)T * P * sizeof(double), c->stream));
+    // The per-piece and per-tesseroid rows of a slab of points live on the device
+    // ((Q + T) * slab * 8 bytes): the points are processed in slabs that keep that under ~2 GiB.
+    // A row's value at a point does not depend on the slab (one group, pieces summed in order).
+    int64_t slab = (int64_t)((2ull << 30) / ((unsigned long long)(m->n_pieces + T) * sizeof(double)));
+    slab = slab / 512 * 512;
+    if (slab < 512)
+        slab = 512;
+    if (const char *dbg = getenv("TVD_DEBUG_JAC_SLAB"))     // tests force several slabs with this
+        slab = atoll(dbg) > 0 ? atoll(dbg) : slab;
+    if (slab > P)
+        slab = P;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c->pts.reserve((size_t)slab * 4 * sizeof(double), st));
+    CUDA_TRY(c->jac_out.reserve((size_t)T * slab * sizeof(double), st));
     double *d_pts = c->pts.as<double>();
-    const double *src[4] = {lon, sinlat, coslat, radius};
-    for (int k = 0; k < 4; k++)
-        CUDA_TRY(cudaMemcpyAsync(d_pts + (size_t)k * P, src[k], P * sizeof(double),
-                                 cudaMemcpyHostToDevice, c->stream));
-    double *res[1] = {nullptr};
-    rc = forward_core(m, c, fs, P, d_pts, d_pts + P, d_pts + 2 * P, d_pts + 3 * P, stack_size, 1,
-                      res, stats, nullptr, c->stream, RadiusInfo(), c->jac_out.as<double>());
-    if (rc)
-        return rc;
-    CUDA_TRY(cudaMemcpyAsync(jac, c->jac_out.p, (size_t)T * P * sizeof(double),
-                             cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<int64_t> st_slab(TVD_NSTATS, 0);
+    for (int64_t p0 = 0; p0 < P; p0 += slab) {
+        const int64_t n = P - p0 < slab ? P - p0 : slab;
+        const double *src[4] = {lon + p0, sinlat + p0, coslat + p0, radius + p0};
+        for (int k = 0; k < 4; k++)
+            CUDA_TRY(cudaMemcpyAsync(d_pts + (size_t)k * n, src[k], n * sizeof(double),
+                                     cudaMemcpyHostToDevice, st));
+        double *res[1] = {nullptr};
+        rc = forward_core(m, c, fs, n, d_pts, d_pts + n, d_pts + 2 * n, d_pts + 3 * n, stack_size,
+                          1, res, st_slab.data(), nullptr, st, RadiusInfo(),
+                          c->jac_out.as<double>());
+        if (rc)
+            return rc;
+        // rows of the slab [T][n] -> columns p0 .. p0 + n of the caller's [T][P]
+        CUDA_TRY(cudaMemcpy2DAsync(jac + p0, (size_t)P * sizeof(double), c->jac_out.p,
+                                   (size_t)n * sizeof(double), (size_t)n * sizeof(double),
+                                   (size_t)T, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (stats)
+            for (int k = 0; k < TVD_NSTATS; k++)
+                stats[k] += st_slab[k];
+    }
+    if (stats)
+        stats[TVD_ST_PIECES] = m->n_pieces;
     return TVD_OK;
 }

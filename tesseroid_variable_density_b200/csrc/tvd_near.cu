@@ -42,6 +42,7 @@
 #define NW_CAP_LARGE 512
 #define NW_RATIO_SMALL 3.2          // largest ratio served by the small queue
 #define NW_LEAFCAP 64               // leaf buffer entries per warp
+#define NW_CTX 8                    // doubles of per-pair constants kept in shared memory
 #ifndef NW_WARPS
 #define NW_WARPS 4                  // warps per block
 #endif
@@ -69,6 +70,7 @@ struct NwWarp {                     // per-warp shared-memory state
     // bits 8-: 1 + the reference's stktop after this node was popped
     int meta[NW_CAP];
     double lw[NW_LEAFCAP], le[NW_LEAFCAP], ls[NW_LEAFCAP], ln[NW_LEAFCAP];
+    double ctx[NW_CTX];             // lon sinlat coslat radius rt rtop ratio of the current pair
 };
 
 struct PairCtx {                    // what a (piece, point) pair contributes to every node
@@ -84,15 +86,13 @@ struct PairCtx {                    // what a (piece, point) pair contributes to
 // distance_n_size + divisions (_tesseroid.pyx:104-146) of one cell: returns nlon-1 | (nlat-1) << 1,
 // and bit 2 when the cell should split but is below the 0.1 m floor (the reference's error
 // count).  Out of line: it is called for the roots and inside the walk.
-struct NodeTest {
-    int code;       // nlon-1 | (nlat-1) << 1 | too-small << 2
-    float key;      // ratio * max(Llon, Llat) / distance: >= 1 for a cell that splits, and the
-                    // larger the deeper its subtree (an estimate, used for scheduling only)
-};
-static __device__ __noinline__ NodeTest node_test_call(double w, double e, double s, double n,
-                                                       double lon, double sinlat, double coslat,
-                                                       double radius, double rt, double rtop,
-                                                       double ratio)
+// distance_n_size + divisions (_tesseroid.pyx:104-146) of one cell: returns nlon-1 | (nlat-1) << 1,
+// and bit 2 when the cell should split but is below the 0.1 m floor (the reference's error
+// count).  *key (optional) = ratio * max(Llon, Llat) / distance: >= 1 for a cell that splits, and
+// the larger the deeper its subtree (an estimate, used for scheduling only).
+__device__ __forceinline__ int node_test_body(double w, double e, double s, double n, double lon,
+                                              double sinlat, double coslat, double radius,
+                                              double rt, double rtop, double ratio, float *key)
 {
     const double lont = TVD_D2R * 0.5 * (w + e);
     const double latt = TVD_D2R * 0.5 * (s + n);
@@ -104,27 +104,27 @@ static __device__ __noinline__ NodeTest node_test_call(double w, double e, doubl
     NW_SINCOS(TVD_D2R * s, sin_s, cos_s);
     const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * NW_COS(TVD_D2R * (e - w)));
     const double Llat = rtop * acos(sin_n * sin_s + cos_n * cos_s);
-    NodeTest r;
-    r.code = 0;
+    int code = 0;
     const bool near_lon = distance <= ratio * Llon, near_lat = distance <= ratio * Llat;
     // the reference overwrites error = -1, so a cell too small in both dimensions counts once
     const bool small_lon = near_lon && Llon <= 0.1, small_lat = near_lat && Llat <= 0.1;
     if (near_lon && !small_lon)
-        r.code |= 1;
+        code |= 1;
     if (near_lat && !small_lat)
-        r.code |= 2;
+        code |= 2;
     if (small_lon || small_lat)
-        r.code |= 4;
-    r.key = (float)(ratio * fmax(Llon, Llat)) / (float)distance;
-    return r;
+        code |= 4;
+    if (key)
+        *key = (float)(ratio * fmax(Llon, Llat)) / (float)distance;
+    return code;
 }
-__device__ __forceinline__ int node_test(const PairCtx &c, double w, double e, double s, double n,
-                                         int &too_small)
+// Out-of-line form for the walk.  The pair's constants travel through the warp's shared memory
+// (NwWarp::ctx): eleven doubles by value would spill to the local-memory stack at every call.
+static __device__ __noinline__ int node_test_call(double w, double e, double s, double n,
+                                                  const double *ctx)
 {
-    const NodeTest r = node_test_call(w, e, s, n, c.lon, c.sinlat, c.coslat, c.radius, c.rt,
-                                      c.rtop, c.ratio);
-    too_small += (r.code >> 2) & 1;
-    return r.code & 3;
+    return node_test_body(w, e, s, n, ctx[0], ctx[1], ctx[2], ctx[3], ctx[4], ctx[5], ctx[6],
+                          nullptr);
 }
 
 // scale_nodes (_tesseroid.pyx:152-176) + kernel{V,x,y,z}[_variable] (:231-520) and the Fatiando 0.5
@@ -275,22 +275,28 @@ near_roots(const NearArgs a)
         make_pair_ctx(a, pi, q, t, c, dens0, dens1);
         const double w = a.table.tess_bounds[6 * t + 0], e = a.table.tess_bounds[6 * t + 1];
         const double s = a.table.tess_bounds[6 * t + 2], n = a.table.tess_bounds[6 * t + 3];
-        const NodeTest r = node_test_call(w, e, s, n, c.lon, c.sinlat, c.coslat, c.radius, c.rt,
-                                          c.rtop, c.ratio);
-        code = r.code & 3;
-        small = (r.code >> 2) & 1;
+        float depth_key = 0.f;
+        const int r = node_test_body(w, e, s, n, c.lon, c.sinlat, c.coslat, c.radius, c.rt, c.rtop,
+                                     c.ratio, &depth_key);
+        code = r & 3;
+        small = (r >> 2) & 1;
         if (code == 0) {
             a.pair_result[i] = leaf_glq<FIELD>(c, w, e, s, n);
         } else {
             if (-1 + (code == 3 ? 4 : 2) > c.stack_size)
                 overflow = true;        // stktop + new_cells > STACK_SIZE at the root (:88)
             int ex = 0;
-            frexpf(r.key, &ex);         // key in [2^(ex-1), 2^ex)
+            frexpf(depth_key, &ex);     // key in [2^(ex-1), 2^ex)
             klass = ex < 0 ? 0 : (ex > 31 ? 31 : ex);
-            atomicAdd(a.bins + klass, 1u);
         }
         a.root_code[i] = (unsigned char)code;
         a.root_class[i] = (unsigned char)klass;
+    }
+    {
+        // one atomic per (warp, class): a slab's millions of pairs fall into two or three classes
+        const unsigned peers = __match_any_sync(NW_FULL, klass);
+        if (klass <= 31 && (threadIdx.x & 31) == __ffs(peers) - 1)
+            atomicAdd(a.bins + klass, (unsigned)__popc(peers));
     }
     const unsigned m_have = __ballot_sync(NW_FULL, have);
     const unsigned m_leaf = __ballot_sync(NW_FULL, have && code == 0);
@@ -323,12 +329,15 @@ near_order(const NearArgs a)
     }
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_pairs)
-        return;
-    const int k = a.root_class[i];
-    if (k > 31)
-        return;
-    a.order[start[k] + atomicAdd(a.bins + 32 + k, 1u)] = (int32_t)i;
+    const int k = i < a.n_pairs ? a.root_class[i] : 255;
+    const unsigned peers = __match_any_sync(NW_FULL, k);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (k <= 31 && lane == leader)
+        base = atomicAdd(a.bins + 32 + k, (unsigned)__popc(peers));
+    base = __shfl_sync(NW_FULL, base, leader);
+    if (k <= 31)
+        a.order[start[k] + base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)i;
 }
 
 template <int FIELD, int NW_CAP>
@@ -375,6 +384,13 @@ near_walk(const NearArgs a)
                 bool queue_full = false;
                 __syncwarp();
                 if (lane == 0) {
+                    S.ctx[0] = c.lon;
+                    S.ctx[1] = c.sinlat;
+                    S.ctx[2] = c.coslat;
+                    S.ctx[3] = c.radius;
+                    S.ctx[4] = c.rt;
+                    S.ctx[5] = c.rtop;
+                    S.ctx[6] = c.ratio;
                     S.w[0] = a.table.tess_bounds[6 * t + 0];
                     S.e[0] = a.table.tess_bounds[6 * t + 1];
                     S.s[0] = a.table.tess_bounds[6 * t + 2];
@@ -429,8 +445,11 @@ near_walk(const NearArgs a)
                             head = (head + k) & (NW_CAP - 1);
                         count -= k;
                         int code = 0, small = 0;
-                        if (valid)
-                            code = node_test(c, cw, ce, cs, cn, small);
+                        if (valid) {
+                            const int r = node_test_call(cw, ce, cs, cn, S.ctx);
+                            code = r & 3;
+                            small = (r >> 2) & 1;
+                        }
                         const bool split = valid && code != 0;
                         const bool leaf = valid && code == 0;
                         if (split) {

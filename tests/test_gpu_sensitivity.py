@@ -34,3 +34,14 @@ def test_unit_density_sensitivity_is_linear_in_density():
     mesh.addprop("density", list(rho))
     want = tesseroid.gz(lons, lats, heights, mesh)
     assert np.max(np.abs(A @ rho - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+def test_point_slabs_do_not_change_the_rows(monkeypatch):
+    """tvd_sensitivity walks large point sets in slabs (device memory for (Q + T) x slab values);
+    a row's value at a point must not depend on the slab it fell into."""
+    mesh = cases.exponential_case(1e4, 10)[0]
+    lats, lons, heights = gridder.regular((-80, 80, 0, 355), (40, 50), z=2000.)     # 2000 points
+    whole = tesseroid.sensitivity("gz", lons, lats, heights, mesh, delta=0.1)
+    monkeypatch.setenv("TVD_DEBUG_JAC_SLAB", "512")
+    slabs = tesseroid.sensitivity("gz", lons, lats, heights, mesh, delta=0.1)
+    assert np.array_equal(whole, slabs)
