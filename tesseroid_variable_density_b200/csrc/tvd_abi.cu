@@ -1,6 +1,7 @@
 // tvd_abi.cu -- the C ABI of libtvd.so (include/tvd.h): model handles, per-device contexts,
 // workspaces and the orchestration  K1 -> K4 -> Phase A -> sort -> Phase B -> Phase C.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -163,7 +164,7 @@ static void free_table(PieceTable &t, cudaStream_t stream)
     t = PieceTable();
 }
 
-static void free_ctx(DeviceCtx *c)
+static void destroy_ctx(DeviceCtx *c)
 {
     if (!c)
         return;
@@ -172,8 +173,7 @@ static void free_ctx(DeviceCtx *c)
     free_table(c->tab, st);
     for (Buf *b : {&c->test_rec, &c->glq_rec, &c->geom, &c->tile_rec, &c->ab_rec, &c->far_out,
                    &c->queue, &c->keys_sorted, &c->pair_result, &c->sort_temp, &c->counters,
-                   &c->near_ws,
-                   &c->pts, &c->result, &c->counts, &c->jac_pieces, &c->jac_out})
+                   &c->near_ws, &c->pts, &c->result, &c->counts, &c->jac_pieces, &c->jac_out})
         b->release(st);
     pinned_put(c->h_pinned);
     if (c->ev0)
@@ -192,6 +192,47 @@ static void free_ctx(DeviceCtx *c)
         cudaStreamDestroy(st);
     }
     delete c;
+}
+
+// Contexts (stream, events, pinned staging, small workspaces) are recycled between models of a
+// process: the field functions build and drop a model per call, and creating a stream and
+// sixteen events costs as much as the whole set-up of a small model.
+#define TVD_CTX_POOL 8                      // recycled contexts kept per device
+#define TVD_CTX_KEEP_BYTES ((size_t)64 << 20)   // workspaces above this size are not kept
+static std::mutex g_ctx_pool_mu;
+static std::vector<DeviceCtx *> g_ctx_pool[64];
+
+static void free_ctx(DeviceCtx *c)
+{
+    if (!c)
+        return;
+    if (c->device < 0 || c->device >= 64 || !c->stream) {
+        destroy_ctx(c);
+        return;
+    }
+    cudaSetDevice(c->device);
+    cudaStream_t st = c->stream;
+    free_table(c->tab, st);                 // stream-ordered: the next user of this stream follows
+    for (Buf *b : {&c->test_rec, &c->glq_rec, &c->geom, &c->tile_rec, &c->ab_rec, &c->far_out,
+                   &c->queue, &c->keys_sorted, &c->pair_result, &c->sort_temp, &c->counters,
+                   &c->near_ws, &c->pts, &c->result, &c->counts, &c->jac_pieces, &c->jac_out})
+        if (b->cap > TVD_CTX_KEEP_BYTES)
+            b->release(st);
+    c->has_table = false;
+    c->glq_packed = false;
+    c->packed_nf = 0;
+    c->packed_ppg = -1;
+    c->ab_packed = false;
+    c->qcap_hint = 0;
+    c->defer_sync = false;
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_pool_mu);
+        if (g_ctx_pool[c->device].size() < TVD_CTX_POOL) {
+            g_ctx_pool[c->device].push_back(c);
+            return;
+        }
+    }
+    destroy_ctx(c);
 }
 
 // the tesseroid table of the model on c's device, uploaded from the given host arrays
@@ -246,6 +287,14 @@ static int new_ctx(int device, DeviceCtx **out)
             done[device] = true;
         }
     }
+    if (device >= 0 && device < 64) {
+        std::lock_guard<std::mutex> lock(g_ctx_pool_mu);
+        if (!g_ctx_pool[device].empty()) {
+            *out = g_ctx_pool[device].back();
+            g_ctx_pool[device].pop_back();
+            return TVD_OK;
+        }
+    }
     DeviceCtx *c = new DeviceCtx();
     c->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -265,7 +314,7 @@ static int new_ctx(int device, DeviceCtx **out)
             e = cudaErrorMemoryAllocation;
     }
     if (e != cudaSuccess) {
-        free_ctx(c);
+        destroy_ctx(c);
         CUDA_TRY(e);
     }
     *out = c;
@@ -548,6 +597,17 @@ extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int3
         if (kind[i] < TVD_DENS_CONST || kind[i] > TVD_DENS_SINE)
             return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_model_create: unknown density kind");
 
+    // TVD_DEBUG_TIMING=1 prints the host time of each stage (development aid)
+    const bool timing = getenv("TVD_DEBUG_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[tvd_model_create] %-28s %8.1f us\n", what,
+                std::chrono::duration<double, std::micro>(now - t_prev).count());
+        t_prev = now;
+    };
     DeviceGuard guard;
     tvd_model *m = new tvd_model();
     m->n_tess = n_tess;
@@ -561,6 +621,7 @@ extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int3
         delete m;
         return rc;
     }
+    lap("context (stream, events)");
     cudaStream_t st = c->stream;
     int *d_status = nullptr;
     int64_t *d_offsets = nullptr;
@@ -577,6 +638,7 @@ extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int3
     rc = upload_tess(m, c, bounds, kind, params);
     if (rc)
         return fail(rc);
+    lap("tesseroid table upload");
 #define MODEL_TRY(expr)                                                                  \
     do {                                                                                 \
         cudaError_t _e = (expr);                                                         \
@@ -599,7 +661,9 @@ extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int3
     MODEL_TRY(cudaMemcpyAsync(h_total, d_offsets + n_tess, sizeof(int64_t), cudaMemcpyDeviceToHost,
                               st));
     MODEL_TRY(cudaMemcpyAsync(h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    lap("K1 count + scan enqueued");
     MODEL_TRY(cudaStreamSynchronize(st));      // the host pages of bounds/kind/params are free again
+    lap("synchronise");
     const int64_t total = *h_total;
     const int status = *h_status;
     if (status != 0) {
@@ -624,6 +688,7 @@ extern "C" int tvd_model_create(int64_t n_tess, const double *bounds, const int3
     // no synchronisation here: everything that uses the table is ordered after it, either on
     // this stream or behind a synchronisation of it (get_ctx, forward_core)
     MODEL_TRY(cudaEventRecord(c->ev_ready, st));
+    lap("K1 emit enqueued");
 #undef MODEL_TRY
     c->has_table = true;
     m->ctx[device] = c;

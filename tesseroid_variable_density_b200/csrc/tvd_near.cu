@@ -251,19 +251,25 @@ __device__ __forceinline__ void pair_densities(const NearArgs &a, int64_t q, int
 }
 
 // Roots, one THREAD per pair: the literal test of the root cell.  A root that does not split
-// after all (the sweep's far test is conservative) is integrated here; the others are filed by
-// the estimated depth of their tree (class = exponent of ratio*L/d), so that the walk can start
-// with the deepest trees -- they are orders of magnitude longer than the median and would
-// otherwise finish alone at the end.
+// after all (the sweep's far test is conservative) is integrated here.  A root that splits but
+// is barely near-field (class 1: ratio*L/d < 2) usually has only leaves below it -- the
+// millions of shallow pairs of a regional grid a few km above the model: its children are
+// tested here too and, if none of them splits, integrated here, in the walk's own summation
+// order (leaf n on lane n, butterfly: (v0 + v2) + (v1 + v3)), so a pair's bits do not depend
+// on which kernel finished it.  Everything else is filed by the estimated depth of its tree
+// (class = exponent of ratio*L/d), so that the walk can start with the deepest trees -- they are
+// orders of magnitude longer than the median and would otherwise finish alone at the end.
 //   ws layout: code[n] (uint8: split code, 0 = done), klass[n] (uint8), order[n] (int32),
 //   bins[64] (uint32: [0..31] pairs per class, [32..63] scatter cursors)
 template <int FIELD>
 __global__ void __launch_bounds__(128)
 near_roots(const NearArgs a)
 {
+    __shared__ double s_ctx[128][NW_CTX + 1];       // + 1: rows on different banks
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool have = i < a.n_pairs;
     int code = 0, small = 0, klass = 255;
+    unsigned nodes = 0, leaves = 0, splits = 0, rootleaf = 0;
     bool overflow = false;
     if (have) {
         const unsigned long long key = a.keys[i];
@@ -280,14 +286,62 @@ near_roots(const NearArgs a)
                                      c.ratio, &depth_key);
         code = r & 3;
         small = (r >> 2) & 1;
+        nodes = 1;
         if (code == 0) {
             a.pair_result[i] = leaf_glq<FIELD>(c, w, e, s, n);
+            leaves = rootleaf = 1;
         } else {
-            if (-1 + (code == 3 ? 4 : 2) > c.stack_size)
+            const int cells = code == 3 ? 4 : 2;
+            if (-1 + cells > c.stack_size)
                 overflow = true;        // stktop + new_cells > STACK_SIZE at the root (:88)
             int ex = 0;
             frexpf(depth_key, &ex);     // key in [2^(ex-1), 2^ex)
             klass = ex < 0 ? 0 : (ex > 31 ? 31 : ex);
+            if (klass <= 1 && !overflow) {
+                double *ctx = s_ctx[threadIdx.x];
+                ctx[0] = c.lon;
+                ctx[1] = c.sinlat;
+                ctx[2] = c.coslat;
+                ctx[3] = c.radius;
+                ctx[4] = c.rt;
+                ctx[5] = c.rtop;
+                ctx[6] = c.ratio;
+                // split (:187-195): children in push order (i, j) = (0,0),(0,1),(1,0),(1,1)
+                const int nlon = 1 + (code & 1), nlat = 1 + ((code >> 1) & 1);
+                const double dlon = (e - w) / nlon, dlat = (n - s) / nlat;
+                bool shallow = true;
+                int csmall = 0;
+                for (int ch = 0; ch < cells && shallow; ch++) {
+                    const int ci = nlat == 2 ? (ch >> 1) : ch, cj = ch - ci * nlat;
+                    const int rr = node_test_call(w + ci * dlon, w + (ci + 1) * dlon, s + cj * dlat,
+                                                  s + (cj + 1) * dlat, ctx);
+                    shallow = (rr & 3) == 0;
+                    csmall += (rr >> 2) & 1;
+                }
+                if (shallow) {
+                    double v[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+                    for (int ch = 0; ch < cells; ch++) {
+                        const int ci = nlat == 2 ? (ch >> 1) : ch, cj = ch - ci * nlat;
+                        const double val = leaf_glq<FIELD>(c, w + ci * dlon, w + (ci + 1) * dlon,
+                                                           s + cj * dlat, s + (cj + 1) * dlat);
+                        if (ch == 0) v[0] = val;
+                        else if (ch == 1) v[1] = val;
+                        else if (ch == 2) v[2] = val;
+                        else v[3] = val;
+                    }
+                    // the walk's order: lane n holds leaf n, lanes are added by the butterfly
+                    a.pair_result[i] = cells == 4 ? (v[0] + v[2]) + (v[1] + v[3]) : v[0] + v[1];
+                    nodes += cells;
+                    leaves += cells;
+                    splits = 1;
+                    small += csmall;
+                    if (a.leaf_counts)
+                        atomicAdd(&a.leaf_counts[t * a.n_points + pi], cells - 1);
+                    klass = 255;
+                    code = 0;
+                }
+            }
         }
         a.root_code[i] = (unsigned char)code;
         a.root_class[i] = (unsigned char)klass;
@@ -298,16 +352,20 @@ near_roots(const NearArgs a)
         if (klass <= 31 && (threadIdx.x & 31) == __ffs(peers) - 1)
             atomicAdd(a.bins + klass, (unsigned)__popc(peers));
     }
-    const unsigned m_have = __ballot_sync(NW_FULL, have);
-    const unsigned m_leaf = __ballot_sync(NW_FULL, have && code == 0);
+    const unsigned n_nodes = __reduce_add_sync(NW_FULL, nodes);
+    const unsigned n_leaves = __reduce_add_sync(NW_FULL, leaves);
+    const unsigned n_splits = __reduce_add_sync(NW_FULL, splits);
+    const unsigned n_rootleaf = __reduce_add_sync(NW_FULL, rootleaf);
     const unsigned n_small = __reduce_add_sync(NW_FULL, (unsigned)small);
     const bool any_over = __any_sync(NW_FULL, overflow);
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&a.counters[0], (unsigned long long)__popc(m_have));
-        if (m_leaf) {
-            atomicAdd(&a.counters[1], (unsigned long long)__popc(m_leaf));
-            atomicAdd(&a.counters[5], (unsigned long long)__popc(m_leaf));
-        }
+        atomicAdd(&a.counters[0], (unsigned long long)n_nodes);
+        if (n_leaves)
+            atomicAdd(&a.counters[1], (unsigned long long)n_leaves);
+        if (n_splits)
+            atomicAdd(&a.counters[2], (unsigned long long)n_splits);
+        if (n_rootleaf)
+            atomicAdd(&a.counters[5], (unsigned long long)n_rootleaf);
         if (n_small)
             atomicAdd(&a.counters[3], (unsigned long long)n_small);
         if (any_over)
