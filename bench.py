@@ -462,9 +462,9 @@ def run_gpu(args):
     if irr is not None:
         irr.close()
 
-    ms_strong, identical, g_full, lo, hi = None, None, None, 0, 0
+    ms_strong, identical, g_full, lo, hi, strong_clocks = None, None, None, 0, 0, None
     if "strong" in legs:
-        ms_strong, identical, g_full, lo, hi = strong_leg(
+        ms_strong, identical, g_full, lo, hi, strong_clocks = strong_leg(
             torch, dist, lib, timer, prepared, device_call, to_device, _convert_coords, lons, lats,
             heights, world, rank, dev)
     # ---- cold end to end: tesseroid.gz(lon, lat, height, model, njobs=N) from a Python model
@@ -558,7 +558,7 @@ def run_gpu(args):
                        "value": strong_value, "unit": UNIT, "seconds": ms_strong * 1e-3,
                        "points_per_gpu": int(hi - lo), "sweep_groups": int(g_full),
                        "efficiency_vs_weak_rate": strong_value / value,
-                       "sharding_bit_identical": identical},
+                       "sharding_bit_identical": identical, "clocks": strong_clocks},
             "sharding_bit_identical": identical,
             "e2e_cold": e2e_cold,
             "gpu_launches": launches, "clocks": clocks, "checksum": checksum,
@@ -581,7 +581,7 @@ def run_gpu(args):
 def strong_leg(torch, dist, lib, timer, prepared, device_call, to_device, _convert_coords, lons,
                lats, heights, world, rank, dev):
     """Fixed-size (strong) scaling: the WHOLE 1000 x 1000 grid split over the ranks, one pass;
-    then the sharding check.  Returns (ms, bit_identical, n_groups, lo, hi)."""
+    then the sharding check.  Returns (ms, bit_identical, n_groups, lo, hi, clocks)."""
     n_total = lons.size
     # contiguous chunks as _split_arrays (tesseroid.py:318-323), global summation plan
     from tesseroid_variable_density_b200.distributed import shard_bounds
@@ -590,7 +590,11 @@ def strong_leg(torch, dist, lib, timer, prepared, device_call, to_device, _conve
     full_pts = to_device(_convert_coords(lons[lo:hi], lats[lo:hi], heights[lo:hi]))
     full_res = torch.empty(hi - lo, dtype=torch.float64, device=dev)
     device_call(prepared, resident_small(full_pts, 4096), full_res[:4096], 4096, g_full)   # warm-up
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
     ms_strong = timer.run(lambda i: device_call(prepared, full_pts, full_res, hi - lo, g_full), 1)
+    strong_clocks = sampler.stop() if rank == 0 else None
     # sharding check: rank 0 recomputes the first 4096 points of every rank's chunk (and, with
     # one rank, a chunk that starts off a multiple of 32) and compares the bits
     probe = 4096
@@ -613,7 +617,7 @@ def strong_leg(torch, dist, lib, timer, prepared, device_call, to_device, _conve
     del full_pts
 
     del full_res
-    return ms_strong, identical, g_full, lo, hi
+    return ms_strong, identical, g_full, lo, hi, strong_clocks
 
 
 def resident_small(pts, n):

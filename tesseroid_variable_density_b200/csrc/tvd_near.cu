@@ -90,19 +90,34 @@ struct PairCtx {                    // what a (piece, point) pair contributes to
 // and bit 2 when the cell should split but is below the 0.1 m floor (the reference's error
 // count).  *key (optional) = ratio * max(Llon, Llat) / distance: >= 1 for a cell that splits, and
 // the larger the deeper its subtree (an estimate, used for scheduling only).
+template <bool VEC>
 __device__ __forceinline__ int node_test_body(double w, double e, double s, double n, double lon,
                                               double sinlat, double coslat, double radius,
                                               double rt, double rtop, double ratio, float *key)
 {
     const double lont = TVD_D2R * 0.5 * (w + e);
     const double latt = TVD_D2R * 0.5 * (s + n);
-    double sinlatt, coslatt, sin_n, cos_n, sin_s, cos_s;
-    NW_SINCOS(latt, sinlatt, coslatt);
-    const double cospsi = sinlat * sinlatt + coslat * coslatt * NW_COS(lon - lont);
+    double sinlatt, coslatt, sin_n, cos_n, sin_s, cos_s, cos_dlon, cos_ew;
+    if (VEC) {
+        // the five sin/cos arguments of a node are known up front: one batched evaluation (five
+        // interleaved dependency chains) instead of five calls in a row -- the walk of a deep
+        // pair is a chain of dependent steps, its latency is what counts
+        const double arg[5] = {latt, TVD_D2R * n, TVD_D2R * s, lon - lont, TVD_D2R * (e - w)};
+        double sv[5], cv[5];
+        cr_sincos_vec<5>(arg, sv, cv);
+        sinlatt = sv[0], coslatt = cv[0], sin_n = sv[1], cos_n = cv[1];
+        sin_s = sv[2], cos_s = cv[2], cos_dlon = cv[3], cos_ew = cv[4];
+    } else {
+        // one thread per pair (near_roots): registers matter more than latency
+        NW_SINCOS(latt, sinlatt, coslatt);
+        NW_SINCOS(TVD_D2R * n, sin_n, cos_n);
+        NW_SINCOS(TVD_D2R * s, sin_s, cos_s);
+        cos_dlon = NW_COS(lon - lont);
+        cos_ew = NW_COS(TVD_D2R * (e - w));
+    }
+    const double cospsi = sinlat * sinlatt + coslat * coslatt * cos_dlon;
     const double distance = sqrt(radius * radius + rt * rt - 2 * radius * rt * cospsi);
-    NW_SINCOS(TVD_D2R * n, sin_n, cos_n);
-    NW_SINCOS(TVD_D2R * s, sin_s, cos_s);
-    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * NW_COS(TVD_D2R * (e - w)));
+    const double Llon = rtop * acos(sinlatt * sinlatt + (coslatt * coslatt) * cos_ew);
     const double Llat = rtop * acos(sin_n * sin_s + cos_n * cos_s);
     int code = 0;
     const bool near_lon = distance <= ratio * Llon, near_lat = distance <= ratio * Llat;
@@ -120,17 +135,18 @@ __device__ __forceinline__ int node_test_body(double w, double e, double s, doub
 }
 // Out-of-line form for the walk.  The pair's constants travel through the warp's shared memory
 // (NwWarp::ctx): eleven doubles by value would spill to the local-memory stack at every call.
+template <bool VEC>
 static __device__ __noinline__ int node_test_call(double w, double e, double s, double n,
                                                   const double *ctx)
 {
-    return node_test_body(w, e, s, n, ctx[0], ctx[1], ctx[2], ctx[3], ctx[4], ctx[5], ctx[6],
-                          nullptr);
+    return node_test_body<VEC>(w, e, s, n, ctx[0], ctx[1], ctx[2], ctx[3], ctx[4], ctx[5], ctx[6],
+                               nullptr);
 }
 
 // scale_nodes (_tesseroid.pyx:152-176) + kernel{V,x,y,z}[_variable] (:231-520) and the Fatiando 0.5
 // tensor integrands for one leaf cell.  cos psi and l^2 keep the reference's operation order;
 // l^-1 comes from the MUFU seed + one third-order correction instead of sqrt and a division.
-template <int FIELD>
+template <int FIELD, bool VEC>
 __device__ __forceinline__ double leaf_glq(const PairCtx &c, double w, double e, double s, double n)
 {
     constexpr bool NEED_SIN = FIELD == TVD_GY || FIELD == TVD_GXY || FIELD == TVD_GYY ||
@@ -138,6 +154,24 @@ __device__ __forceinline__ double leaf_glq(const PairCtx &c, double w, double e,
     const double dlon = e - w, dlat = n - s;
     const double mlon = 0.5 * (e + w), mlat = 0.5 * (n + s);
     double coslon[2], sinlon[2], sinlatc[2], coslatc[2];
+    if (VEC) {
+        // sin(lonc - lon) = -sin(lon - lonc) exactly (odd function, same |argument|)   (:401)
+        double arg[4], sv[4], cv[4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double node = i == 0 ? -TVD_NODE : TVD_NODE;
+            arg[i] = TVD_D2R * (0.5 * dlat * node + mlat);
+            arg[2 + i] = c.lon - TVD_D2R * (0.5 * dlon * node + mlon);
+        }
+        cr_sincos_vec<4>(arg, sv, cv);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            sinlatc[i] = sv[i];
+            coslatc[i] = cv[i];
+            coslon[i] = cv[2 + i];
+            sinlon[i] = NEED_SIN ? -sv[2 + i] : 0.0;
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const double node = i == 0 ? -TVD_NODE : TVD_NODE;
@@ -153,6 +187,7 @@ __device__ __forceinline__ double leaf_glq(const PairCtx &c, double w, double e,
             coslon[i] = NW_COS(c.lon - lonc);
             sinlon[i] = 0.0;
         }
+    }
     }
     const double scale = TVD_D2R * dlon * TVD_D2R * dlat * c.dr * 0.125;
     double result = 0.0;
@@ -282,13 +317,13 @@ near_roots(const NearArgs a)
         const double w = a.table.tess_bounds[6 * t + 0], e = a.table.tess_bounds[6 * t + 1];
         const double s = a.table.tess_bounds[6 * t + 2], n = a.table.tess_bounds[6 * t + 3];
         float depth_key = 0.f;
-        const int r = node_test_body(w, e, s, n, c.lon, c.sinlat, c.coslat, c.radius, c.rt, c.rtop,
-                                     c.ratio, &depth_key);
+        const int r = node_test_body<false>(w, e, s, n, c.lon, c.sinlat, c.coslat, c.radius, c.rt,
+                                            c.rtop, c.ratio, &depth_key);
         code = r & 3;
         small = (r >> 2) & 1;
         nodes = 1;
         if (code == 0) {
-            a.pair_result[i] = leaf_glq<FIELD>(c, w, e, s, n);
+            a.pair_result[i] = leaf_glq<FIELD, false>(c, w, e, s, n);
             leaves = rootleaf = 1;
         } else {
             const int cells = code == 3 ? 4 : 2;
@@ -313,8 +348,8 @@ near_roots(const NearArgs a)
                 int csmall = 0;
                 for (int ch = 0; ch < cells && shallow; ch++) {
                     const int ci = nlat == 2 ? (ch >> 1) : ch, cj = ch - ci * nlat;
-                    const int rr = node_test_call(w + ci * dlon, w + (ci + 1) * dlon, s + cj * dlat,
-                                                  s + (cj + 1) * dlat, ctx);
+                    const int rr = node_test_call<false>(w + ci * dlon, w + (ci + 1) * dlon,
+                                                         s + cj * dlat, s + (cj + 1) * dlat, ctx);
                     shallow = (rr & 3) == 0;
                     csmall += (rr >> 2) & 1;
                 }
@@ -323,7 +358,7 @@ near_roots(const NearArgs a)
 #pragma unroll 1
                     for (int ch = 0; ch < cells; ch++) {
                         const int ci = nlat == 2 ? (ch >> 1) : ch, cj = ch - ci * nlat;
-                        const double val = leaf_glq<FIELD>(c, w + ci * dlon, w + (ci + 1) * dlon,
+                        const double val = leaf_glq<FIELD, false>(c, w + ci * dlon, w + (ci + 1) * dlon,
                                                            s + cj * dlat, s + (cj + 1) * dlat);
                         if (ch == 0) v[0] = val;
                         else if (ch == 1) v[1] = val;
@@ -398,8 +433,11 @@ near_order(const NearArgs a)
         a.order[start[k] + base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)i;
 }
 
+#ifndef NW_MINBLOCKS
+#define NW_MINBLOCKS 2              // resident blocks per SM the register allocation is sized for
+#endif
 template <int FIELD, int NW_CAP>
-__global__ void __launch_bounds__(32 * NW_WARPS)
+__global__ void __launch_bounds__(32 * NW_WARPS, NW_MINBLOCKS)
 near_walk(const NearArgs a)
 {
     extern __shared__ __align__(16) unsigned char nw_smem[];
@@ -504,7 +542,7 @@ near_walk(const NearArgs a)
                         count -= k;
                         int code = 0, small = 0;
                         if (valid) {
-                            const int r = node_test_call(cw, ce, cs, cn, S.ctx);
+                            const int r = node_test_call<true>(cw, ce, cs, cn, S.ctx);
                             code = r & 3;
                             small = (r >> 2) & 1;
                         }
@@ -548,7 +586,7 @@ near_walk(const NearArgs a)
                     if (nleaf >= 32 || (count == 0 && nleaf > 0)) {
                         const int m = nleaf < 32 ? nleaf : 32;
                         if (lane < m)
-                            acc += leaf_glq<FIELD>(c, S.lw[lane], S.le[lane], S.ls[lane], S.ln[lane]);
+                            acc += leaf_glq<FIELD, true>(c, S.lw[lane], S.le[lane], S.ls[lane], S.ln[lane]);
                         __syncwarp();
                         const int rest = nleaf - m;         // < 32: no overlap with the slots read
                         double mw = 0, me = 0, ms = 0, mn = 0;

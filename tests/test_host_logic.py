@@ -248,3 +248,25 @@ def test_analytical_shells_consistent():
         integral = np.sum(0.5 * (f[1:] + f[:-1]) * np.diff(rr))
         v = 4 * np.pi * G * integral / (6378137.0 + height)
         assert np.isclose(v, exact["potential"], rtol=1e-8)
+
+
+def test_sediment_thickness_reader_and_neuquen_layer():
+    """datasets.load_sediment_thickness reads data/sediment_thickness.dat the way the reference
+    does (numpy.loadtxt(..., unpack=True), data/README.md:25-37, neuquen_basin.py:33-47) and
+    neuquen_basin_model builds the layer of neuquen_basin.py:55-72; both must agree with the
+    fixture the golden replays use."""
+    import cases
+    from tesseroid_variable_density_b200 import datasets
+    sed = datasets.load_sediment_thickness()
+    fix = np.load(os.path.join(cases.GOLDEN, "neuquen_thickness.npz"))
+    assert sed["shape"] == (117, 91) and sed["lat"].size == 117 * 91
+    for k in ("lat", "lon", "thickness"):
+        assert np.array_equal(sed[k], fix[k], equal_nan=True)
+    assert sed["area"] == (sed["lat"].min(), sed["lat"].max(), sed["lon"].min(), sed["lon"].max())
+    basin, top, bottom = datasets.neuquen_basin_model()
+    basin2, top2, bottom2 = cases.neuquen_model()
+    assert (top, bottom) == (top2, bottom2)
+    assert np.array_equal(basin.flat_bounds()[0], basin2.flat_bounds()[0])
+    nans = np.isnan(sed["thickness"])
+    assert int(nans.sum()) == 5692          # degenerate top = bottom = 0 cells, still evaluated
+    assert np.all(basin.top[nans] == 0) and np.all(basin.bottom[nans] == 0)
