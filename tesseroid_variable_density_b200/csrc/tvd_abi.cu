@@ -354,10 +354,21 @@ static int get_ctx(tvd_model *m, int device, DeviceCtx **out)
         src = m->ctx[m->primary];
     }
     // replicate outside the model lock so that several devices are populated concurrently
+    const bool timing = getenv("TVD_DEBUG_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[get_ctx dev %d] %-32s %9.1f us\n", device, what,
+                std::chrono::duration<double, std::micro>(now - t_prev).count());
+        t_prev = now;
+    };
     DeviceCtx *c = nullptr;
     int rc = new_ctx(device, &c);
     if (rc)
         return rc;
+    lap("new_ctx (context, stream, events)");
     {
         // the source finishes its own records first; its stream signals when they are complete
         std::lock_guard<std::mutex> lock(src->mu);
@@ -369,13 +380,16 @@ static int get_ctx(tvd_model *m, int device, DeviceCtx **out)
         }
         if (e == cudaSuccess && !rc)
             e = cudaSetDevice(device);
+        lap("source records ready (lock + K4)");
         if (e == cudaSuccess && !rc) {
             int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can)
+            if (!getenv("TVD_NO_PEER_ACCESS") &&
+                cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can)
                 cudaDeviceEnablePeerAccess(src->device, 0);     // "already enabled" is fine
             cudaGetLastError();
             e = cudaStreamWaitEvent(c->stream, src->ev_ready, 0);
         }
+        lap("peer access");
         if (e != cudaSuccess && !rc) {
             g_last_error = std::string("piece table replication failed: ") + cudaGetErrorString(e);
             rc = (int)e;
@@ -420,8 +434,10 @@ static int get_ctx(tvd_model *m, int device, DeviceCtx **out)
             if (e == cudaSuccess)
                 c->glq_packed = true;
         }
+        lap("copies enqueued");
         if (e == cudaSuccess)
             e = cudaStreamSynchronize(st);      // once per (model, device)
+        lap("copies done");
         if (e != cudaSuccess) {
             g_last_error = std::string("piece table replication failed: ") + cudaGetErrorString(e);
             cudaGetLastError();
@@ -1339,6 +1355,18 @@ static int forward_host(int n_fields, const int *fields, const double *ratios, t
         // are created concurrently, the records arrive by device-to-device copies): a worker that
         // already computes would otherwise hold the source context's lock for its whole sweep.
         {
+            const auto t0 = std::chrono::steady_clock::now();
+            struct Lap {
+                std::chrono::steady_clock::time_point t0;
+                int n;
+                ~Lap()
+                {
+                    if (getenv("TVD_DEBUG_TIMING"))
+                        fprintf(stderr, "[tvd_forward] prepare phase on %d devices %9.1f us\n", n,
+                                std::chrono::duration<double, std::micro>(
+                                    std::chrono::steady_clock::now() - t0).count());
+                }
+            } lap_prepare{t0, nparts};
             std::vector<std::thread> threads;
             for (int d = 0; d < nparts; d++)
                 threads.emplace_back([&, d]() {
@@ -1355,11 +1383,17 @@ static int forward_host(int n_fields, const int *fields, const double *ratios, t
                     return rcs[d];
                 }
         }
+        const bool timing = getenv("TVD_DEBUG_TIMING") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> threads;
         for (int d = 0; d < nparts; d++)
             threads.emplace_back(work, d);
         for (auto &t : threads)
             t.join();
+        if (timing)
+            fprintf(stderr, "[tvd_forward] compute phase on %d devices %9.1f us\n", nparts,
+                    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0)
+                        .count());
     }
     for (int d = 0; d < nparts; d++)
         if (rcs[d]) {
