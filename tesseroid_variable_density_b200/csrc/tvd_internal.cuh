@@ -312,6 +312,7 @@ struct NearArgs {
     int32_t *leaf_counts;            // NULL or [n_tess][n_points]
     int64_t n_points;
     int batch;                       // pairs per work grab (set by the launcher)
+    int shallow;                     // root kernel also finishes barely-near pairs (set by the launcher)
     void *workspace;                 // tvd_near_workspace_bytes(n_pairs) bytes
     // carved out of the workspace by the launcher
     unsigned char *root_code, *root_class;

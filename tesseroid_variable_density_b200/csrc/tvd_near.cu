@@ -332,7 +332,7 @@ near_roots(const NearArgs a)
             int ex = 0;
             frexpf(depth_key, &ex);     // key in [2^(ex-1), 2^ex)
             klass = ex < 0 ? 0 : (ex > 31 ? 31 : ex);
-            if (klass <= 1 && !overflow) {
+            if (klass <= 1 && !overflow && a.shallow) {
                 double *ctx = s_ctx[threadIdx.x];
                 ctx[0] = c.lon;
                 ctx[1] = c.sinlat;
@@ -697,6 +697,10 @@ static cudaError_t launch_near_field(NearArgs a, cudaStream_t stream)
     cudaError_t e = cudaMemsetAsync(a.bins, 0, 64 * sizeof(unsigned), stream);
     if (e != cudaSuccess)
         return e;
+    // The root kernel's one-level expansion pays when there are millions of barely-near pairs; on
+    // a small problem it only lengthens the kernel by its few threads that take it.  Either way
+    // the pair gets the same bits (the walk's own summation order), so this is a free choice.
+    a.shallow = a.n_pairs >= 65536 ? 1 : 0;
     near_roots<FIELD><<<(unsigned)((a.n_pairs + 127) / 128), 128, 0, stream>>>(a);
     near_order<<<(unsigned)((a.n_pairs + 255) / 256), 256, 0, stream>>>(a);
     tvd_count_launch(3);
