@@ -32,6 +32,7 @@
 // Pairs arrive sorted by (point, piece); Phase C adds a point's pair results in piece order,
 // which makes every point's value independent of how the points were sharded over blocks, groups
 // or GPUs.
+#include <cstdlib>
 #include "tvd_internal.cuh"
 
 // queue entries per warp (powers of two): the breadth-first frontier holds ~2 x pi D^2 splitting
@@ -701,6 +702,8 @@ static cudaError_t launch_near_field(NearArgs a, cudaStream_t stream)
     // a small problem it only lengthens the kernel by its few threads that take it.  Either way
     // the pair gets the same bits (the walk's own summation order), so this is a free choice.
     a.shallow = a.n_pairs >= 65536 ? 1 : 0;
+    if (const char *dbg = getenv("TVD_DEBUG_SHALLOW"))     // tests force either way with this
+        a.shallow = dbg[0] == '1' ? 1 : 0;
     near_roots<FIELD><<<(unsigned)((a.n_pairs + 127) / 128), 128, 0, stream>>>(a);
     near_order<<<(unsigned)((a.n_pairs + 255) / 256), 256, 0, stream>>>(a);
     tvd_count_launch(3);

@@ -150,3 +150,20 @@ def test_one_height_specialisation_is_bit_exact(big):
                         np.append(coslat, coslat[0]), np.append(radius, radius[0] + 123.0), pm, 2.5)
     assert np.array_equal(mixed[:n], uniform)
     pm.close()
+
+
+def test_root_kernel_expansion_gives_the_walks_bits(big, monkeypatch):
+    """Barely-near pairs (root splits once, children are leaves) are finished by the root kernel
+    when the queue is large and by the warp walk otherwise; both must return the same bits and
+    counters (the root kernel sums the <= 4 leaves in the walk's butterfly order)."""
+    bounds, cc = big
+    dens = D.ExponentialDensity.between(-412, -275, 845.0, -5155.0, 3)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("TVD_DEBUG_SHALLOW", flag)
+        pm = PreparedModel(flat_with(bounds, dens), delta=0.1)
+        out[flag] = forward_raw("gz", *cc, pm, 2.5, return_stats=True)
+        pm.close()
+    assert out["0"][1]["near_pairs"] > 10000
+    assert out["0"][1] == out["1"][1]
+    assert np.array_equal(out["0"][0], out["1"][0])
