@@ -91,7 +91,7 @@ struct DeviceCtx {
     bool glq_packed = false;
     int packed_nf = 0;
     double packed_ratio[TVD_MAX_FUSED] = {0};
-    Buf test_rec, glq_rec, geom, tile_rec, ab_rec;
+    Buf test_rec, glq_rec, geom, tile_rec, ab_rec, wz_rec;
     bool ab_packed = false;
     double ab_radius = 0.0;
     Buf far_out, queue, keys_sorted, pair_result, sort_temp, counters, near_ws;
@@ -171,7 +171,7 @@ static void destroy_ctx(DeviceCtx *c)
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
     free_table(c->tab, st);
-    for (Buf *b : {&c->test_rec, &c->glq_rec, &c->geom, &c->tile_rec, &c->ab_rec, &c->far_out,
+    for (Buf *b : {&c->test_rec, &c->glq_rec, &c->geom, &c->tile_rec, &c->ab_rec, &c->wz_rec, &c->far_out,
                    &c->queue, &c->keys_sorted, &c->pair_result, &c->sort_temp, &c->counters,
                    &c->near_ws, &c->pts, &c->result, &c->counts, &c->jac_pieces, &c->jac_out})
         b->release(st);
@@ -213,7 +213,7 @@ static void free_ctx(DeviceCtx *c)
     cudaSetDevice(c->device);
     cudaStream_t st = c->stream;
     free_table(c->tab, st);                 // stream-ordered: the next user of this stream follows
-    for (Buf *b : {&c->test_rec, &c->glq_rec, &c->geom, &c->tile_rec, &c->ab_rec, &c->far_out,
+    for (Buf *b : {&c->test_rec, &c->glq_rec, &c->geom, &c->tile_rec, &c->ab_rec, &c->wz_rec, &c->far_out,
                    &c->queue, &c->keys_sorted, &c->pair_result, &c->sort_temp, &c->counters,
                    &c->near_ws, &c->pts, &c->result, &c->counts, &c->jac_pieces, &c->jac_out})
         if (b->cap > TVD_CTX_KEEP_BYTES)
@@ -929,7 +929,7 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
     // pinned landing area of the device counters (TVD_PINNED_HEAD bytes)
     unsigned long long *h_cnt = reinterpret_cast<unsigned long long *>(c->h_pinned) + 8;
     // points at one height: 2r*rc and r^2 + rc^2 per piece instead of per pair
-    const double *d_ab = nullptr;
+    const double *d_ab = nullptr, *d_wz = nullptr;
     if (!d_jac_out) {
         if (rinfo.uniform < 0) {
             int *d_flag = reinterpret_cast<int *>(d_cnt + 7);
@@ -945,12 +945,15 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
         if (rinfo.uniform == 1 && rinfo.r0 == rinfo.r0) {
             if (!c->ab_packed || memcmp(&c->ab_radius, &rinfo.r0, sizeof(double)) != 0) {
                 CUDA_TRY(c->ab_rec.reserve((size_t)Q * TVD_AB_REC * sizeof(double), stream));
+                CUDA_TRY(c->wz_rec.reserve((size_t)Q * TVD_WZ_REC * sizeof(double), stream));
                 CUDA_TRY(tvd_launch_pack_ab(c->tab, c->glq_rec.as<double>(), rinfo.r0,
-                                            c->ab_rec.as<double>(), stream));
+                                            c->ab_rec.as<double>(), c->wz_rec.as<double>(),
+                                            stream));
                 c->ab_packed = true;
                 c->ab_radius = rinfo.r0;
             }
             d_ab = c->ab_rec.as<double>();
+            d_wz = c->wz_rec.as<double>();
         }
     }
     CUDA_TRY(c->far_out.reserve((size_t)nf * n_groups * P * sizeof(double), stream));
@@ -990,6 +993,7 @@ static int forward_core(tvd_model *m, DeviceCtx *c, const FieldSet &fs, int64_t 
         fa.glq_rec = c->glq_rec.as<double>();
         fa.tile_rec = c->tile_rec.as<double>();
         fa.ab_rec = d_ab;
+        fa.wz_rec = d_wz;
         fa.n_groups = n_groups;
         fa.pieces_per_group = ppg;
         fa.tiles_per_group = (int)tiles_per_group;

@@ -170,6 +170,10 @@ struct MaskTraits {
     static constexpr bool needs_y5 = (MASK >> TVD_GXX) != 0;
     static constexpr bool needs_dz = (MASK & ((1 << TVD_GZ) | (1 << TVD_GXZ) | (1 << TVD_GYZ) |
                                               (1 << TVD_GZZ))) != 0;
+    // gz is the only user of dz: w*dz = (w*rc)*cospsi - w*r is formed directly from per-piece
+    // weights (one FMA per node instead of an FMA and a product)
+    static constexpr bool fold_dz = (MASK & (1 << TVD_GZ)) != 0 &&
+                                    (MASK & ((1 << TVD_GXZ) | (1 << TVD_GYZ) | (1 << TVD_GZZ))) == 0;
     static constexpr bool needs_dx = (MASK & ((1 << TVD_GXX) | (1 << TVD_GXY) | (1 << TVD_GXZ))) != 0;
     static constexpr bool needs_dy = (MASK & ((1 << TVD_GXY) | (1 << TVD_GYY) | (1 << TVD_GYZ))) != 0;
 };
@@ -235,7 +239,8 @@ __device__ __forceinline__ void glq_lat(const PointRegs &pt, const double *__res
 // piece's contribution to each field (kernel units, reference sign conventions).
 template <int MASK, bool UR>
 __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__restrict__ g,
-                                           const double *__restrict__ ab, const Angular &A,
+                                           const double *__restrict__ ab,
+                                           const double *__restrict__ wz, const Angular &A,
                                            double *__restrict__ out)
 {
     typedef MaskTraits<MASK> T;
@@ -273,6 +278,28 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
                 wy[j][k] = wx[j][k] * A.clc[j];                // kappa*rc[k]*coslatc*sinlon  (:408)
             }
     }
+    // gz alone needs dz only inside w*dz = w*(rc*cospsi - radius) (:487): with wr = w*rc and
+    // wq = w*radius per (j, k) it is ONE FMA per node, fma(wr, cospsi, -wq).  Points at one height
+    // get wr and wq precomputed with the tile (same products, same roundings).
+    double wr[2][2], wq[2][2];
+    if (T::fold_dz) {
+        if (UR) {
+            const double2 r0 = *reinterpret_cast<const double2 *>(wz + 0);
+            const double2 r1 = *reinterpret_cast<const double2 *>(wz + 2);
+            const double2 q0 = *reinterpret_cast<const double2 *>(wz + 4);
+            const double2 q1 = *reinterpret_cast<const double2 *>(wz + 6);
+            wr[0][0] = r0.x, wr[0][1] = r0.y, wr[1][0] = r1.x, wr[1][1] = r1.y;
+            wq[0][0] = q0.x, wq[0][1] = q0.y, wq[1][0] = q1.x, wq[1][1] = q1.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    wr[j][k] = wjk[j][k] * rck[k];
+                    wq[j][k] = wjk[j][k] * pt.r;
+                }
+        }
+    }
 
     double sum[T::nf];
 #pragma unroll
@@ -301,7 +328,7 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
                 }
                 // rc*cospsi - radius (:487); the product is not ill-conditioned enough to need
                 // the reference's separate rounding (<= 5e-14 relative)
-                if (T::needs_dz)
+                if (T::needs_dz && !T::fold_dz)
                     dz = fma(rck[k], cospsi, -pt.r);
                 if (T::needs_dx)
                     dx = rck[k] * A.kphi[i][j];
@@ -321,7 +348,10 @@ __device__ __forceinline__ void glq_radial(const PointRegs &pt, const double *__
                 }
                 if (mask_has(MASK, TVD_GZ)) {
                     double &acc = sum[mask_slot(MASK, TVD_GZ)];
-                    acc = fma(-(w * dz), y3, acc);                          // z down (:490)
+                    if (T::fold_dz)
+                        acc = fma(-fma(wr[j][k], cospsi, -wq[j][k]), y3, acc);
+                    else
+                        acc = fma(-(w * dz), y3, acc);                      // z down (:490)
                 }
                 // gradient tensor (Fatiando 0.5 integrands, z up)
                 if (mask_has(MASK, TVD_GXX)) {
@@ -369,6 +399,17 @@ __device__ __forceinline__ void add_if_gt(double &acc, double v, double lhs, dou
         : "d"(v), "d"(lhs), "d"(rhs));
 }
 
+// shared-memory layout of one sweep instantiation (doubles per stage, bytes in all)
+template <int MASK, bool UR>
+struct FarSmem {
+    static constexpr int n_test = TVD_TILE * MaskTraits<MASK>::trec;
+    static constexpr int n_glq = TVD_TILE * TVD_GLQ_REC;
+    static constexpr int n_ab = UR ? TVD_TILE * TVD_AB_REC : 0;
+    static constexpr int n_wz = (UR && MaskTraits<MASK>::fold_dz) ? TVD_TILE * TVD_WZ_REC : 0;
+    static constexpr int n_doubles = 2 * (n_test + n_glq + n_ab + n_wz);
+    static constexpr size_t bytes = (size_t)n_doubles * sizeof(double) + 2 * sizeof(uint64_t);
+};
+
 template <int MASK, int THREADS, int MINBLOCKS, bool JAC, bool UR>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 far_sweep(const FarArgs a)
@@ -376,10 +417,20 @@ far_sweep(const FarArgs a)
     typedef MaskTraits<MASK> T;
     constexpr int NF = T::nf;
     constexpr int TREC = T::trec;
-    __shared__ __align__(16) double s_test[2][TVD_TILE * TREC];
-    __shared__ __align__(16) double s_glq[2][TVD_TILE * TVD_GLQ_REC];
-    __shared__ __align__(16) double s_ab[2][UR ? TVD_TILE * TVD_AB_REC : 2];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    // dynamic shared memory (some field sets exceed the 48 KB of static shared memory):
+    // two stages of test, GLQ, one-height (a, b) and one-height (w*rc, w*r) records, two mbarriers
+    typedef FarSmem<MASK, UR> L;
+    extern __shared__ __align__(16) unsigned char far_smem[];
+    double *const s_base = reinterpret_cast<double *>(far_smem);
+    // stage st of each record kind (pointer arithmetic, not pointer arrays: those would live in
+    // local memory)
+    auto s_test = [&](int st) { return s_base + st * L::n_test; };
+    auto s_glq = [&](int st) { return s_base + 2 * L::n_test + st * L::n_glq; };
+    auto s_ab = [&](int st) { return s_base + 2 * (L::n_test + L::n_glq) + st * L::n_ab; };
+    auto s_wz = [&](int st) {
+        return s_base + 2 * (L::n_test + L::n_glq + L::n_ab) + st * L::n_wz;
+    };
+    uint64_t *const s_bar = reinterpret_cast<uint64_t *>(s_base + L::n_doubles);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -430,11 +481,14 @@ far_sweep(const FarArgs a)
         const uint32_t bt = (uint32_t)(nq * TREC * sizeof(double));
         const uint32_t bg = (uint32_t)(nq * TVD_GLQ_REC * sizeof(double));
         const uint32_t ba = UR ? (uint32_t)(nq * TVD_AB_REC * sizeof(double)) : 0u;
-        mbar_expect_tx(&s_bar[st], bt + bg + ba);
-        bulk_g2s(s_test[st], a.test_rec + q0 * TREC, bt, &s_bar[st]);
-        bulk_g2s(s_glq[st], a.glq_rec + q0 * TVD_GLQ_REC, bg, &s_bar[st]);
+        const uint32_t bw = (UR && T::fold_dz) ? (uint32_t)(nq * TVD_WZ_REC * sizeof(double)) : 0u;
+        mbar_expect_tx(&s_bar[st], bt + bg + ba + bw);
+        bulk_g2s(s_test(st), a.test_rec + q0 * TREC, bt, &s_bar[st]);
+        bulk_g2s(s_glq(st), a.glq_rec + q0 * TVD_GLQ_REC, bg, &s_bar[st]);
         if (UR)
-            bulk_g2s(s_ab[st], a.ab_rec + q0 * TVD_AB_REC, ba, &s_bar[st]);
+            bulk_g2s(s_ab(st), a.ab_rec + q0 * TVD_AB_REC, ba, &s_bar[st]);
+        if (UR && T::fold_dz)
+            bulk_g2s(s_wz(st), a.wz_rec + q0 * TVD_WZ_REC, bw, &s_bar[st]);
     };
 
     if (tid == 0) {
@@ -449,9 +503,10 @@ far_sweep(const FarArgs a)
         mbar_wait(&s_bar[st], (uint32_t)((tile >> 1) & 1));
         const int64_t q0 = q_begin + (int64_t)tile * TVD_TILE;
         int nq = (int)((q_end - q0) < TVD_TILE ? (q_end - q0) : TVD_TILE);
-        const double *tt = s_test[st];
-        const double *gg = s_glq[st];
-        const double *aa = s_ab[st];
+        const double *tt = s_test(st);
+        const double *gg = s_glq(st);
+        const double *aa = s_ab(st);
+        const double *ww = s_wz(st);
         // d^2-part of the far test of piece qi, computed one piece ahead so that its dependent
         // FMA chain overlaps the radial work of the previous piece
         // conservative far-field test: d^2 - thr_f^2 = r^2 + (rt^2 - thr_f^2) - 2 p.c > 0 with
@@ -496,7 +551,8 @@ far_sweep(const FarArgs a)
                 if (flags.x == 0)
                     glq_lat<MASK>(pt, grec, ang);
                 double v[NF];
-                glq_radial<MASK, UR>(pt, grec, aa + (UR ? qi * TVD_AB_REC : 0), ang, v);
+                glq_radial<MASK, UR>(pt, grec, aa + (UR ? qi * TVD_AB_REC : 0),
+                                     ww + ((UR && T::fold_dz) ? qi * TVD_WZ_REC : 0), ang, v);
                 if (JAC) {
                     if (valid)
                         a.jac[reinterpret_cast<const long long *>(grec)[15] * a.n_points + pidx] = v[0];
@@ -554,7 +610,8 @@ far_sweep(const FarArgs a)
                 if (flags.x == 0)
                     glq_lat<MASK>(pt, grec, ang);
                 double v[NF];
-                glq_radial<MASK, UR>(pt, grec, aa + (UR ? qi * TVD_AB_REC : 0), ang, v);
+                glq_radial<MASK, UR>(pt, grec, aa + (UR ? qi * TVD_AB_REC : 0),
+                                     ww + ((UR && T::fold_dz) ? qi * TVD_WZ_REC : 0), ang, v);
                 if (JAC) {
                     // sensitivity mode: one value per (piece, point); NaN marks a deferred pair
                     if (valid)
@@ -664,23 +721,43 @@ cudaError_t tvd_launch_queue_only(const FarArgs &a, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+template <int MASK, bool JAC, bool UR>
+static cudaError_t launch_sweep(const FarArgs &a, cudaStream_t stream)
+{
+    constexpr int THREADS = TVD_FAR_THREADS;
+    constexpr size_t smem = FarSmem<MASK, UR>::bytes;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return e;
+    if (dev < 0 || dev >= 64)
+        return cudaErrorInvalidDevice;
+    if (!configured[dev]) {
+        e = cudaFuncSetAttribute(far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, JAC, UR>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+        configured[dev] = true;
+    }
+    dim3 grid((unsigned)((a.n_points + THREADS - 1) / THREADS), (unsigned)a.n_groups);
+    far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, JAC, UR><<<grid, THREADS, smem, stream>>>(a);
+    tvd_count_launch();
+    return cudaGetLastError();
+}
+
 template <int MASK>
 static cudaError_t launch_mask(const FarArgs &a, cudaStream_t stream)
 {
-    constexpr int THREADS = TVD_FAR_THREADS;
-    dim3 grid((unsigned)((a.n_points + THREADS - 1) / THREADS), (unsigned)a.n_groups);
     if (a.jac != nullptr) {
         if constexpr (mask_count(MASK) == 1)
-            far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, true, false><<<grid, THREADS, 0, stream>>>(a);
+            return launch_sweep<MASK, true, false>(a, stream);
         else
             return cudaErrorInvalidValue;
-    } else if (a.ab_rec != nullptr) {
-        far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, false, true><<<grid, THREADS, 0, stream>>>(a);
-    } else {
-        far_sweep<MASK, THREADS, TVD_FAR_MINBLOCKS, false, false><<<grid, THREADS, 0, stream>>>(a);
     }
-    tvd_count_launch();
-    return cudaGetLastError();
+    if (a.ab_rec != nullptr)
+        return launch_sweep<MASK, false, true>(a, stream);
+    return launch_sweep<MASK, false, false>(a, stream);
 }
 
 #define TVD_M(f) (1 << (f))

@@ -258,8 +258,11 @@ cudaError_t tvd_launch_pack_tiles(const PieceTable &t, const double *d_geom, Rat
                                   cudaStream_t stream);
 // points-at-one-height specialisation: per piece 2r*rc0 2r*rc1 r^2+rc0^2 r^2+rc1^2 (sweep order)
 #define TVD_AB_REC 4
+// ... and, for gz, the node weights times rc[k] and times the radius:
+// w00*rc0 w01*rc1 w10*rc0 w11*rc1  w00*r w01*r w10*r w11*r (sweep order)
+#define TVD_WZ_REC 8
 cudaError_t tvd_launch_pack_ab(const PieceTable &t, const double *d_glq, double radius,
-                               double *d_ab, cudaStream_t stream);
+                               double *d_ab, double *d_wz, cudaStream_t stream);
 // *d_flag = 1 if every radius[i] is bitwise equal to radius[0], else 0
 cudaError_t tvd_launch_check_uniform(int64_t n, const double *d_radius, int *d_flag,
                                      cudaStream_t stream);
@@ -272,6 +275,7 @@ struct FarArgs {
     int64_t n_pieces;
     const double *test_rec, *glq_rec, *tile_rec;
     const double *ab_rec;            // non-NULL: all points share one radius (see TVD_AB_REC)
+    const double *wz_rec;            // with ab_rec: TVD_WZ_REC
     int n_groups;
     int64_t pieces_per_group;
     int tiles_per_group;             // ceil(pieces_per_group / TVD_TILE)

@@ -762,7 +762,7 @@ cudaError_t tvd_debug_math_launch(int func, int64_t n, const double *d_x, double
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k4_pack_ab(int64_t n_pieces, const double *__restrict__ glq_rec, double radius,
-           double *__restrict__ ab)
+           double *__restrict__ ab, double *__restrict__ wz)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_pieces)
@@ -775,15 +775,24 @@ k4_pack_ab(int64_t n_pieces, const double *__restrict__ glq_rec, double radius,
     o[1] = r2 * g[7];
     o[2] = r_sqr + g[8];
     o[3] = r_sqr + g[9];
+    // w[j][k]*rc[k] and w[j][k]*radius, the products the sweep forms for points at individual heights
+    double *z = wz + TVD_WZ_REC * q;
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            z[2 * j + k] = g[10 + 2 * j + k] * g[6 + k];
+            z[4 + 2 * j + k] = g[10 + 2 * j + k] * radius;
+        }
 }
 
 cudaError_t tvd_launch_pack_ab(const PieceTable &t, const double *d_glq, double radius,
-                               double *d_ab, cudaStream_t stream)
+                               double *d_ab, double *d_wz, cudaStream_t stream)
 {
     if (t.n_pieces == 0)
         return cudaSuccess;
     k4_pack_ab<<<(unsigned)((t.n_pieces + 255) / 256), 256, 0, stream>>>(t.n_pieces, d_glq, radius,
-                                                                        d_ab);
+                                                                        d_ab, d_wz);
     tvd_count_launch();
     return cudaGetLastError();
 }

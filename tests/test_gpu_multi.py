@@ -82,3 +82,29 @@ def test_chunking_is_bit_exact_when_warps_straddle_pi_over_4(field):
         assert np.array_equal(bad[keep], one[keep])
     finally:
         pm.close()
+
+
+@pytest.mark.parametrize("field", ["gz", "potential", "gx", "gzz"])
+def test_one_height_specialisation_returns_the_general_bits(field):
+    """Points at one height take a specialised sweep (per-piece constants precomputed with the
+    same roundings, tvd_far.cu `UR`).  A chunk of a mixed-height point set may be uniform while
+    the whole set is not, so the two instantiations must return the same bits -- otherwise
+    sharding would change values."""
+    from tesseroid_variable_density_b200 import density as D
+    from tesseroid_variable_density_b200 import gridder
+    from tesseroid_variable_density_b200.mesher import TesseroidMesh
+    from tesseroid_variable_density_b200.tesseroid import PreparedModel, _convert_coords, forward_raw
+    mesh = TesseroidMesh((-5, 5, -4, 4, 0, -30000.), (1, 16, 20))
+    mesh.addprop("density", [D.ExponentialDensity.between(2670, 3300, 0., -30000., 3)] * mesh.size)
+    lats, lons, heights = gridder.regular((-8, 8, -9, 9), (20, 30), z=40e3)      # 600 points
+    heights = heights.copy()
+    heights[300:] = 55e3                                   # second half at another height
+    cc = _convert_coords(lons, lats, heights)
+    pm = PreparedModel(mesh, delta=0.1)
+    ratio = cases.DEFAULT_RATIO[field]
+    try:
+        mixed = forward_raw(field, *cc, pm, ratio)                         # general sweep
+        halves = forward_raw(field, *cc, pm, ratio, devices=[0, 0])       # two uniform chunks
+        assert np.array_equal(mixed, halves), int(np.sum(mixed != halves))
+    finally:
+        pm.close()
