@@ -41,9 +41,9 @@ NLAT = NLON = 1000
 SEED = 20190277
 # FP64 flops of one far-field gz (piece, point) pair, FMA = 2.
 #  * F_PAIR_EXECUTED: what the far-field sweep of THIS build executes per pair, from the ncu
-#    capture committed with it (profiles/far_sweep_r1g.md: 11.4 DADD + 44.7 DMUL + 40.3 DFMA =
-#    136.7 flops; smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on x elapsed cycles /
-#    pairs).  `roofline.achieved` uses this figure: it is the hardware flop rate of the kernel
+#    capture committed with it (profiles/far_sweep_r2.md: 11.4 DADD + 36.7 DMUL + 40.3 DFMA =
+#    88.4 instructions = 128.8 flops; round 1: 96.4 instructions = 136.7 flops;
+#    smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on x elapsed cycles / pairs).  `roofline.achieved` uses this figure: it is the hardware flop rate of the kernel
 #    and can be checked against ncu directly.  It must be re-measured when the kernel changes.
 #  * SURVEY.md section 8d (convention v1) ESTIMATED 384 = F_test 76 + F_glq 308 from guessed
 #    special-function weights and asked for a one-time ncu calibration on the first kernel; that
@@ -51,14 +51,14 @@ SEED = 20190277
 #    Later kernels do the same pairs with fewer operations (cheaper test and cos, angular work
 #    shared between pieces), so rates computed with 218 or 384 exceed what the hardware executes;
 #    they are reported beside `achieved`, not as `achieved`.
-F_PAIR_EXECUTED = 136.7
+F_PAIR_EXECUTED = 128.8
 F_PAIR_CALIBRATED = 218
 F_PAIR_V1_ESTIMATE = 384
 # static facts of the committed far-field kernel from its ncu capture (profiles/far_sweep_r2.md)
-FAR_TRAFFIC_BYTES = 370.1e6
-FAR_NCU = {"fp64_pipe_pct_of_peak": 86.8, "issue_active_pct": 59.9,
-           "executed_fp64_instructions_per_piece_pair": 96.4,
-           "executed_flops_per_piece_pair": 136.7}
+FAR_TRAFFIC_BYTES = 562.7e6
+FAR_NCU = {"fp64_pipe_pct_of_peak": 83.9, "issue_active_pct": 59.7,
+           "executed_fp64_instructions_per_piece_pair": 88.4,
+           "executed_flops_per_piece_pair": 128.8}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -530,7 +530,8 @@ def run_gpu(args):
                          "frac": (achieved / peak) if (achieved and peak > 0) else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this
                          # kernel at the default shape (ncu --set full, profiles/far_sweep_r2.md);
-                         # the algorithmic minimum is the piece records read once, 337 MB
+                         # the algorithmic minimum is the piece records read once (449 MB) plus
+                         # the group sums written once (78 MB)
                          "traffic": FAR_TRAFFIC_BYTES if P == 75776 else None,
                          "kernel": "far_sweep<gz>",
                          "kernel_ms_per_launch": far_ms / max(1.0, nfar),
@@ -538,8 +539,8 @@ def run_gpu(args):
                          "flops_per_piece_pair": F_PAIR_EXECUTED,
                          "piece_pairs_per_launch": far_pairs / max(1.0, nfar),
                          # the instruction mix (DADD/DMUL count 1 flop, DFMA 2) caps the flop
-                         # fraction of a saturated FP64 pipe at 136.7 / (2 x 96.4) = 0.71
-                         "frac_ceiling_of_this_instruction_mix": 0.71,
+                         # fraction of a saturated FP64 pipe at 128.8 / (2 x 88.4) = 0.73
+                         "frac_ceiling_of_this_instruction_mix": 0.73,
                          "achieved_with_first_kernel_count_218": achieved_cal,
                          "achieved_with_survey_estimate_384": achieved_v1,
                          "peak_source": "DFMA microbenchmark run by this process "
