@@ -67,8 +67,6 @@ struct Buf {
             cudaFreeAsync(p, stream);
         p = nullptr;
         cap = 0;
-        // grow geometrically past the first allocation: repeated calls with slowly growing
-        // sizes do not reallocate every time
         cudaError_t e = cudaMallocAsync(&p, bytes, stream);
         if (e == cudaSuccess)
             cap = bytes;
