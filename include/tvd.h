@@ -237,7 +237,8 @@ int tvd_debug_trig(int device, int64_t n, const double *x, double *cos_out, doub
 /* Debug/test hook: the double-double sin (func 0), cos (1) and exp (2) that K1 uses for the
  * density samples (tesseroid.py:259,294), and the table-based correctly rounded sin (3), cos (4)
  * and sincos (5: its sine, 6: its cosine) of the near-field walk (the values glibc returned to
- * the reference at _tesseroid.pyx:113-121,168-169,242), evaluated on `device` for n host values. */
+ * the reference at _tesseroid.pyx:113-121,168-169,242) and the table-based correctly rounded
+ * exp (7) of K1/K4, evaluated on `device` for n host values. */
 int tvd_debug_math(int device, int func, int64_t n, const double *x, double *out);
 
 #ifdef __cplusplus

@@ -13,7 +13,7 @@ mkdir -p $OBJ
 pids=()
 for f in tvd_preprocess tvd_far tvd_near tvd_sort tvd_abi; do
   stale=0
-  for dep in $f.cu tvd_internal.cuh tvd_ddmath.cuh tvd_crtrig.cuh tvd_sincos_table.inc ../../include/tvd.h build.sh; do
+  for dep in $f.cu tvd_internal.cuh tvd_ddmath.cuh tvd_crtrig.cuh tvd_sincos_table.inc tvd_exp_table.inc ../../include/tvd.h build.sh; do
     if [ ! -f $OBJ/$f.o ] || [ $dep -nt $OBJ/$f.o ]; then stale=1; fi
   done
   if [ $stale = 1 ]; then

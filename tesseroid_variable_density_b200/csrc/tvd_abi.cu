@@ -573,7 +573,7 @@ extern "C" int tvd_debug_trig(int device, int64_t n, const double *x, double *co
 extern "C" int tvd_debug_math(int device, int func, int64_t n, const double *x, double *out)
 {
     g_last_error.clear();
-    if (n < 0 || func < 0 || func > 6 || (n > 0 && (!x || !out)))
+    if (n < 0 || func < 0 || func > 7 || (n > 0 && (!x || !out)))
         return set_error(TVD_ERR_BAD_ARGUMENT, "tvd_debug_math: bad argument");
     if (tvd_device_count() <= device || device < 0)
         return set_error(TVD_ERR_NO_DEVICE, "tvd_debug_math: no such CUDA device");

@@ -204,7 +204,7 @@ __device__ __forceinline__ double tvd_density_cr(int kind, const double *__restr
         return p[0] * r + p[2];
     }
     case TVD_DENS_EXP:
-        return p[0] * dd_exp(p[1] * (h - p[2]) / p[3]) + p[4];
+        return p[0] * cr_exp(p[1] * (h - p[2]) / p[3]) + p[4];     // same bits as dd_exp
     default:
         return p[0] * cr_sin(p[1] * h) + p[2];      // same bits as dd_sin (tvd_crtrig.cuh)
     }

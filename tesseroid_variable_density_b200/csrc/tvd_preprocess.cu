@@ -742,7 +742,8 @@ __global__ void debug_math_kernel(int func, int64_t n, const double *__restrict_
     case 3: v = cr_sin(x[i]); break;          // table-based correctly rounded (tvd_crtrig.cuh)
     case 4: v = cr_cos(x[i]); break;
     case 5: { double c; cr_sincos(x[i], v, c); break; }
-    default: { double s; cr_sincos(x[i], s, v); break; }
+    case 6: { double s; cr_sincos(x[i], s, v); break; }
+    default: v = cr_exp(x[i]); break;
     }
     out[i] = v;
 }

@@ -32,6 +32,21 @@ int main(int argc, char **argv)
         printf("range [%g, %g]: n=%ld  not-ok %ld (%.2e)  sin != quad %ld (with ok: %ld)  cos != quad %ld (with ok: %ld)\n",
                rg[0], rg[1], n, notok, (double)notok / n, bad_s, bad_ok_s, bad_c, bad_ok_c);
     }
+    double eranges[][2] = {{-1.0, 1.0}, {-40.0, 5.0}, {-690.0, 690.0}, {-1e-6, 1e-6}};
+    for (auto &rg : eranges) {
+        long bad = 0, notok = 0, bad_ok = 0;
+        for (long i = 0; i < n; i++) {
+            double x = rg[0] + (rg[1] - rg[0]) * rnd();
+            int k; bool ok;
+            double r = cr_exp_core(x, k, ok);
+            double got = scalbn(r, k);
+            double want = (double)expq((__float128)x);
+            if (!ok) notok++;
+            if (got != want) { bad++; if (ok) { bad_ok++; if (bad_ok < 4) printf("  exp x=%a got %a quad %a\n", x, got, want); } }
+        }
+        printf("exp range [%g, %g]: n=%ld  not-ok %ld (%.2e)  exp != quad %ld (with ok: %ld)\n",
+               rg[0], rg[1], n, notok, (double)notok / n, bad, bad_ok);
+    }
     return 0;
 }
 // build: g++ -O2 -ffp-contract=off -mfma crtrig_host_test.cpp -lquadmath -lm

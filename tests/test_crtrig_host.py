@@ -1,6 +1,7 @@
 """
 CPU check of the table-based correctly rounded sin/cos of the near-field walk
-(tesseroid_variable_density_b200/csrc/tvd_crtrig.cuh): its host/device core is compiled by g++
+(tesseroid_variable_density_b200/csrc/tvd_crtrig.cuh), and of the correctly rounded exp of K1/K4:
+their host/device cores are compiled by g++
 and compared with quad precision (libquadmath) rounded to double.  The reference gets these
 values from glibc (_tesseroid.pyx:113-121,168-169,242,401), which was correctly rounded at the
 time of the paper.
@@ -34,3 +35,10 @@ def test_cr_sincos_core_is_correctly_rounded(tmp_path):
         notok, bad_s, bad_ok_s, bad_c, bad_ok_c = (int(g) for g in m.groups())
         assert bad_ok_s == 0 and bad_ok_c == 0, l      # accepted by Ziv's test => correctly rounded
         assert notok <= 400000 * 2e-4, l               # the slow path is taken by ~2e-5 of the calls
+    elines = [l for l in out.splitlines() if l.startswith("exp range")]
+    assert len(elines) == 4
+    for l in elines:
+        m = re.search(r"not-ok (\d+) .*exp != quad (\d+) \(with ok: (\d+)\)", l)
+        notok, bad, bad_ok = (int(g) for g in m.groups())
+        assert bad_ok == 0, l
+        assert notok <= 400000 * 5e-4, l

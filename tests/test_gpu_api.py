@@ -234,6 +234,31 @@ def test_table_trig_equals_double_double():
     assert np.array_equal(run(3)[idx], ms) and np.array_equal(run(4)[idx], mc)
 
 
+def test_table_exp_equals_double_double():
+    """K1/K4's exp (tvd_crtrig.cuh: table + Ziv's rounding test) returns the bits of the
+    double-double version, i.e. the correctly rounded value."""
+    import mpmath
+    mpmath.mp.dps = 60
+    lib = _lib.load()
+    rng = np.random.default_rng(6)
+    x = np.concatenate([rng.uniform(-1, 1, 300000), rng.uniform(-40, 5, 400000),
+                        rng.uniform(-690, 690, 200000), rng.uniform(-1e-6, 1e-6, 50000),
+                        np.array([0.0, -0.0, 1e-300, 1.0, -1.0, 699.9, -699.9, 700.0, 710.0, -745.0,
+                                  -800.0, np.inf, -np.inf, np.nan])])
+    x = np.ascontiguousarray(x)
+
+    def run(func):
+        out = np.empty_like(x)
+        assert lib.tvd_debug_math(0, func, x.size, _lib.ptr_f64(x), _lib.ptr_f64(out)) == 0
+        return out
+    dd, cr = run(2), run(7)
+    same = (dd == cr) | (np.isnan(dd) & np.isnan(cr))
+    assert np.all(same), (int(np.sum(~same)), x[~same][:5])
+    idx = rng.choice(900000, 3000, replace=False)
+    want = np.array([float(mpmath.exp(mpmath.mpf(float(v)))) for v in x[idx]])
+    assert np.array_equal(cr[idx], want)
+
+
 def test_k1_tie_breaking_with_whole_periods(oracle_lib):
     """A sine with a whole number of periods over the tesseroid has mathematically equal maxima
     of |rho_n - line|; the split list is then decided by the last bit of sin()."""
