@@ -1222,21 +1222,17 @@ static RadiusInfo scan_radius(const double *radius, int64_t n)
     return r;
 }
 
-// one device's share of tvd_forward: host slices in, host slices out
-static int forward_host_slice(tvd_model *m, int device, const FieldSet &fs, const int *order,
-                              int n_fields, int64_t P, int64_t p0, int64_t P_total,
-                              const double *lon, const double *sinlat, const double *coslat,
-                              const double *radius, int stack_size, int n_groups,
-                              double *results /*[n_fields][P_total], caller order*/,
-                              int64_t *stats /*[n_fields][TVD_NSTATS], slot order*/,
-                              int32_t *leaf_counts)
+// one pass of one device: points [p0, p0 + P) of the caller's arrays, host slices in, host slices
+// out (the context is locked and its device current)
+static int forward_host_pass(tvd_model *m, DeviceCtx *c, const FieldSet &fs, const int *order,
+                             int n_fields, int64_t P, int64_t p0, int64_t P_total,
+                             const double *lon, const double *sinlat, const double *coslat,
+                             const double *radius, int stack_size, int n_groups,
+                             double *results /*[n_fields][P_total], caller order*/,
+                             int64_t *stats /*[n_fields][TVD_NSTATS], slot order*/,
+                             int32_t *leaf_counts)
 {
-    DeviceCtx *c = nullptr;
-    int rc = get_ctx(m, device, &c);
-    if (rc)
-        return rc;
-    std::lock_guard<std::mutex> lock(c->mu);
-    CUDA_TRY(cudaSetDevice(device));
+    int rc = TVD_OK;
     if (stats)
         memset(stats, 0, (size_t)n_fields * TVD_NSTATS * sizeof(int64_t));
     if (P == 0)
@@ -1298,6 +1294,64 @@ static int forward_host_slice(tvd_model *m, int device, const FieldSet &fs, cons
     if (m->n_pieces == 0)
         return TVD_OK;
     return forward_finish(c, fs, m->n_pieces, P, c->last_nq, stats);
+}
+
+// Points of one pass.  The device buffers that grow with the number of points (points, results,
+// the group sums far[nf][G][P], the near-field queues) are bounded by processing a device's share
+// in slabs, the way the reference streams points one by one (_tesseroid.pyx:65): the group sums
+// stay under 2 GiB and a slab under 2^24 points.  A point's value depends on (point, model,
+// n_groups) only, and n_groups is the plan of the WHOLE job, so slabbing does not change a bit.
+static int64_t point_slab(int nf, int n_groups)
+{
+    int64_t slab = (int64_t)((2ull << 30) / (8ull * (unsigned long long)nf *
+                                             (unsigned long long)(n_groups > 0 ? n_groups : 1)));
+    if (slab > (1ll << 24))
+        slab = 1ll << 24;
+    slab = slab / TVD_FAR_THREADS * TVD_FAR_THREADS;
+    if (slab < TVD_FAR_THREADS)
+        slab = TVD_FAR_THREADS;
+    if (const char *dbg = getenv("TVD_DEBUG_POINT_SLAB"))   // tests force several slabs with this
+        slab = atoll(dbg) > 0 ? atoll(dbg) : slab;
+    return slab;
+}
+
+// one device's share of tvd_forward
+static int forward_host_slice(tvd_model *m, int device, const FieldSet &fs, const int *order,
+                              int n_fields, int64_t P, int64_t p0, int64_t P_total,
+                              const double *lon, const double *sinlat, const double *coslat,
+                              const double *radius, int stack_size, int n_groups,
+                              double *results /*[n_fields][P_total], caller order*/,
+                              int64_t *stats /*[n_fields][TVD_NSTATS], slot order*/,
+                              int32_t *leaf_counts)
+{
+    DeviceCtx *c = nullptr;
+    int rc = get_ctx(m, device, &c);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(c->mu);
+    CUDA_TRY(cudaSetDevice(device));
+    const int64_t slab = point_slab(n_fields, n_groups);
+    if (P <= slab)
+        return forward_host_pass(m, c, fs, order, n_fields, P, p0, P_total, lon, sinlat, coslat,
+                                 radius, stack_size, n_groups, results, stats, leaf_counts);
+    if (stats)
+        memset(stats, 0, (size_t)n_fields * TVD_NSTATS * sizeof(int64_t));
+    std::vector<int64_t> st_pass((size_t)n_fields * TVD_NSTATS, 0);
+    for (int64_t s0 = 0; s0 < P; s0 += slab) {
+        const int64_t n = P - s0 < slab ? P - s0 : slab;
+        rc = forward_host_pass(m, c, fs, order, n_fields, n, p0 + s0, P_total, lon, sinlat, coslat,
+                               radius, stack_size, n_groups, results, stats ? st_pass.data() : nullptr,
+                               leaf_counts);
+        if (rc)
+            return rc;
+        if (stats)
+            for (size_t k = 0; k < st_pass.size(); k++)
+                stats[k] += st_pass[k];
+    }
+    if (stats)
+        for (int f = 0; f < n_fields; f++)
+            stats[(size_t)f * TVD_NSTATS + TVD_ST_PIECES] = m->n_pieces;
+    return TVD_OK;
 }
 
 static int forward_host(int n_fields, const int *fields, const double *ratios, tvd_model *m,

@@ -174,12 +174,15 @@ def flatten_model(model, dens=None):
             kp = override
         else:
             d = tesseroid.props["density"]
-            key = id(d)
-            kp = cache.get(key)
-            if kp is None:
+            # the cache holds the object itself: an id is only unique while its object is alive
+            # (a generator may build a fresh density per tesseroid)
+            hit = cache.get(id(d))
+            if hit is not None:
+                kp = hit[1]
+            else:
                 kp = _density.as_kind_params(d)
                 if isinstance(d, _density.Density):
-                    cache[key] = kp
+                    cache[id(d)] = (d, kp)
         bounds.append(b)
         kinds.append(kp[0])
         params.append(kp[1])

@@ -5,7 +5,8 @@ import pytest
 from tesseroid_variable_density_b200 import density as D
 from tesseroid_variable_density_b200 import gridder, _lib
 from tesseroid_variable_density_b200.model import FlatModel
-from tesseroid_variable_density_b200.tesseroid import PreparedModel, _convert_coords, forward_raw
+from tesseroid_variable_density_b200.tesseroid import (PreparedModel, _convert_coords, forward_raw,
+                                                      forward_raw_fused)
 
 pytestmark = pytest.mark.gpu
 
@@ -167,3 +168,29 @@ def test_root_kernel_expansion_gives_the_walks_bits(big, monkeypatch):
     assert out["0"][1]["near_pairs"] > 10000
     assert out["0"][1] == out["1"][1]
     assert np.array_equal(out["0"][0], out["1"][0])
+
+
+def test_point_slabs_do_not_change_a_bit(big, monkeypatch):
+    """A device's share of the points is processed in slabs that bound the point-proportional
+    device buffers (tvd_abi.cu: point_slab), the way the reference streams points one by one
+    (_tesseroid.pyx:65).  The summation plan is that of the whole job, so values, counters and
+    per-(tesseroid, point) leaf counts of a slabbed run are those of the single pass - also when
+    the slabs are ragged (1000 is not a multiple of the 512-point blocks) and on two chunks."""
+    bounds, cc = big
+    dens = D.ExponentialDensity.between(-412, -275, 845.0, -5155.0, 3)
+    flat = flat_with(bounds[1500:1900], dens)          # rows under the first rows of points
+    n = 5000
+    pts = [c[:n].copy() for c in cc]
+    pm = PreparedModel(flat, delta=0.1)
+    want, swant, cwant = forward_raw("gz", *pts, pm, 2.5, leaf_counts=True)
+    assert swant["near_pairs"] > 100
+    fwant = forward_raw_fused(("potential", "gz", "gzz"), *pts, pm, (1.0, 2.5, 8.0))
+    monkeypatch.setenv("TVD_DEBUG_POINT_SLAB", "1000")
+    got, sgot, cgot = forward_raw("gz", *pts, pm, 2.5, leaf_counts=True)
+    assert np.array_equal(got, want) and sgot == swant and np.array_equal(cgot, cwant)
+    two = forward_raw("gz", *pts, pm, 2.5, devices=[0, 0])
+    assert np.array_equal(two, want)
+    fgot = forward_raw_fused(("potential", "gz", "gzz"), *pts, pm, (1.0, 2.5, 8.0))
+    for name in fwant:
+        assert np.array_equal(fgot[name], fwant[name])
+    pm.close()

@@ -120,6 +120,18 @@ def test_flatten_generic_iterable_follows_check_tesseroid():
         model.flatten_model([bad])
 
 
+def test_flatten_generator_with_short_lived_density_objects():
+    # a generator that builds a fresh density per tesseroid: object ids are recycled as soon as
+    # the previous tesseroid dies, so the per-object cache must not key on a dead object's id
+    def cells():
+        for i in range(200):
+            yield mesher.Tesseroid(i, i + 1, 0, 1, 0, -100,
+                                   props={"density": density.LinearDensity(float(i), 2., 3.)})
+    flat = model.flatten_model(cells())
+    assert flat.size == 200
+    assert flat.params[:, 0].tolist() == [float(i) for i in range(200)]
+
+
 def test_flatten_mesh_fast_path_equals_iteration():
     mesh = mesher.TesseroidMesh((-1, 1, -1, 1, 0, -35000), (2, 3, 3))
     dens = density.ExponentialDensity(1., -1., 0., 1e5, 2.)
