@@ -136,7 +136,10 @@ int tvd_model_get_pieces(const tvd_model *model, double *top, double *bottom, in
  *   stack_size   the reference's STACK_SIZE (tesseroid.py:102); only used to reproduce the
  *                overflow error
  *   n_devices, device_ids   points are split into n_devices contiguous chunks exactly like
- *                _split_arrays (tesseroid.py:318-323); device_ids==NULL means 0..n_devices-1
+ *                _split_arrays (tesseroid.py:318-323); device_ids==NULL means 0..n_devices-1.
+ *                A device works through its chunk in slabs of at most 2^24 points (the reference
+ *                streams points one at a time, _tesseroid.pyx:65), so device memory does not grow
+ *                with P; chunking and slabbing never change a bit of the result
  *   result       [P] OVERWRITTEN with the field in kernel units (the reference accumulates into
  *                a zero-filled array, tesseroid.py:121)
  *   stats        NULL or int64[TVD_NSTATS]
