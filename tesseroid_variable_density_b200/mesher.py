@@ -101,18 +101,19 @@ class TesseroidMesh(object):
     def flat_bounds(self):
         """``(size, 6)`` float64 array of every cell's bounds (same arithmetic as
         ``__getitem__``) and a boolean mask of the cells that are not masked out."""
+        # _cell_bounds' expressions once per column / row / layer, broadcast over the mesh
         nr, nlat, nlon = self.shape
-        index = np.arange(self.size)
-        k = index // (nlon * nlat)
-        j = (index - k * (nlon * nlat)) // nlon
-        i = index - k * (nlon * nlat) - j * nlon
+        w = float(self.bounds[0]) + float(self.dims[0]) * np.arange(nlon)
+        s = float(self.bounds[2]) + float(self.dims[1]) * np.arange(nlat)
+        top = float(self.bounds[4]) + float(self.dims[2]) * np.arange(nr)
         out = np.empty((self.size, 6))
-        out[:, 0] = float(self.bounds[0]) + float(self.dims[0]) * i
-        out[:, 1] = out[:, 0] + float(self.dims[0])
-        out[:, 2] = float(self.bounds[2]) + float(self.dims[1]) * j
-        out[:, 3] = out[:, 2] + float(self.dims[1])
-        out[:, 4] = float(self.bounds[4]) + float(self.dims[2]) * k
-        out[:, 5] = out[:, 4] + float(self.dims[2])
+        cells = out.reshape(nr, nlat, nlon, 6)
+        cells[..., 0] = w
+        cells[..., 1] = w + float(self.dims[0])
+        cells[..., 2] = s[:, np.newaxis]
+        cells[..., 3] = (s + float(self.dims[1]))[:, np.newaxis]
+        cells[..., 4] = top[:, np.newaxis, np.newaxis]
+        cells[..., 5] = (top + float(self.dims[2]))[:, np.newaxis, np.newaxis]
         keep = np.ones(self.size, dtype=bool)
         if len(self.mask):
             keep[np.asarray(self.mask, dtype=int)] = False
@@ -191,16 +192,17 @@ class TesseroidModel(object):
         return Tesseroid(w, e, s, n, self.top[index], self.bottom[index], props)
 
     def flat_bounds(self):
+        # __getitem__'s expressions, evaluated once per column / row and broadcast over the layer
         nlat, nlon = self.shape
         dlat, dlon = self.spacing
-        index = np.arange(self.size)
-        i = index // nlon
-        j = index - i * nlon
+        w = self.lons - dlon / 2.
+        s = self.lats - dlon / 2.        # sic: dlon, as in __getitem__
         out = np.empty((self.size, 6))
-        out[:, 0] = self.lons[j] - dlon / 2.
-        out[:, 1] = out[:, 0] + dlon
-        out[:, 2] = self.lats[i] - dlon / 2.
-        out[:, 3] = out[:, 2] + dlat
+        cells = out.reshape(nlat, nlon, 6)
+        cells[:, :, 0] = w[np.newaxis, :]
+        cells[:, :, 1] = (w + dlon)[np.newaxis, :]
+        cells[:, :, 2] = s[:, np.newaxis]
+        cells[:, :, 3] = (s + dlat)[:, np.newaxis]
         out[:, 4] = self.top
         out[:, 5] = self.bottom
         return out, np.ones(self.size, dtype=bool)
