@@ -543,6 +543,11 @@ def run_gpu(args):
                          # the instruction mix (DADD/DMUL count 1 flop, DFMA 2) caps the flop
                          # fraction of a saturated FP64 pipe at 128.8 / (2 x 88.4) = 0.73
                          "frac_ceiling_of_this_instruction_mix": 0.73,
+                         # measured rate of FP64 INSTRUCTIONS against the bare DFMA loop's (this
+                         # run's `peak`): achieved / peak / (128.8 / (2 x 88.4))
+                         "fp64_instruction_rate_vs_bare_dfma_loop":
+                             (achieved / peak / (F_PAIR_EXECUTED / (2.0 * 88.4)))
+                             if (achieved and peak > 0) else None,
                          "achieved_with_first_kernel_count_218": achieved_cal,
                          "achieved_with_survey_estimate_384": achieved_v1,
                          "peak_source": "DFMA microbenchmark run by this process "
